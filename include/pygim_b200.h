@@ -1,0 +1,161 @@
+/* pygim_b200 - C ABI of libbackend_pim.so (sm_100a).
+ *
+ * This is the drop-in boundary for PyGim's aggregation path (sparse adjacency x dense
+ * features).  In the reference the boundary is a TORCH_LIBRARY(pim_ops, ...) block that is
+ * dlopen()ed through torch.ops.load_library(args.lib_path) (spmm_test.py:111,
+ * inference.py:134); one such library exists per (variant, dtype, format, balance) build.
+ * Here there is ONE library, dtype/format are run-time arguments, and the entry points take
+ * plain pointers and sizes so that any host language can bind them (ctypes in
+ * pygim_b200/_lib.py; INTEGRATION.md shows the stub a PyGim maintainer would add).
+ *
+ * Every function returns 0 on success and a non-zero pygim_status_t otherwise;
+ * pygim_last_error() returns the message for the calling thread.  The reference's failure
+ * mode is assert()/DPU_ASSERT -> abort (spmm_default/spmm_mul_csr.c:136-137,251); here
+ * errors are reported to the caller instead.
+ *
+ * All paths below are relative to /root/reference/backend_pim/.
+ */
+#ifndef PYGIM_B200_H
+#define PYGIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PYGIM_API __attribute__((visibility("default")))
+#else
+#define PYGIM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* val_dt, selected at compile time in the reference: spmm_default/support/common.h:39-60 */
+typedef enum {
+    PYGIM_INT8 = 0,
+    PYGIM_INT16 = 1,
+    PYGIM_INT32 = 2,
+    PYGIM_INT64 = 3,
+    PYGIM_FLT32 = 4,
+    PYGIM_DBL64 = 5
+} pygim_dtype_t;
+
+/* KERNEL=MUL_CSR|MUL_COO in the reference build: spmm_default/CMakeLists.txt:28-30,53-60 */
+typedef enum { PYGIM_CSR = 0, PYGIM_COO = 1 } pygim_format_t;
+
+/* where the caller's buffers live */
+typedef enum { PYGIM_MEM_HOST = 0, PYGIM_MEM_DEVICE = 1 } pygim_mem_t;
+
+typedef enum {
+    PYGIM_OK = 0,
+    PYGIM_ERR_INVALID = 1,   /* bad argument (the reference assert()s: pytorch_api.cpp:212,252,264-266) */
+    PYGIM_ERR_CUDA = 2,      /* a CUDA runtime call failed (the reference DPU_ASSERT -> abort) */
+    PYGIM_ERR_NOT_INIT = 3,  /* dpu_init_* was not called (the reference dereferences a null dpu set) */
+    PYGIM_ERR_NO_DEVICE = 4  /* no sm_100 device visible; there is NO CPU fallback */
+} pygim_status_t;
+
+typedef uint64_t pygim_handle_t;
+
+/* ---------------------------------------------------------------- diagnostics */
+PYGIM_API const char *pygim_last_error(void);
+PYGIM_API int pygim_abi_version(void);
+
+/* ---------------------------------------------------------------- device bring-up
+ * Replaces dpu_init_ranks / dpu_init_dpus / dpu_release
+ *   spmm_default/pytorch_api.cpp:154-164, spmm_grande/pytorch_api.cpp:157-181 (returns dpus_per_rank),
+ *   spmm_multigroup/pytorch_api.cpp:168-178 (groups_per_rank).
+ * A "rank" maps to one (sparse part, dense part) tile of the 2-D partitioning; on the GPU it
+ * is a scheduling unit only.  `device` < 0 keeps the current CUDA device.
+ * units_per_rank_out (may be NULL) receives nr_ranks entries - the analogue of grande's
+ * dpus_per_rank list that grande.py:63-72 uses to deal the feature columns; each entry is the
+ * number of column slices a rank is dealt (= SM count / nr_ranks, at least 1). */
+PYGIM_API int pygim_dpu_init_ranks(int64_t nr_ranks, int64_t groups_per_rank, int device, int32_t *units_per_rank_out);
+PYGIM_API int pygim_dpu_init_dpus(int64_t nr_dpus, int device);
+PYGIM_API int pygim_dpu_release(void);
+
+/* sm count, L2 size, max persisting-L2 bytes, total HBM bytes of the active device */
+PYGIM_API int pygim_device_info(int *device, int *sm_count, int64_t *l2_bytes, int64_t *persisting_l2_max_bytes,
+                      int64_t *hbm_bytes, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------- plan ("to_device_group")
+ * Replaces spmm_csr_to_device_group / spmm_coo_to_device_group
+ *   spmm_default/pytorch_api.cpp:204-243, :286-329 -> ops.hpp:65-92, :121-149
+ *   -> prepare_pim_csr (spmm_mul_csr.c:118-259) / prepare_pim_coo (spmm_mul_coo.c:83-249)
+ *   -> copy_sparse_csr (:261-330) / copy_sparse_coo (spmm_mul_coo.c:251-318)
+ * and spmv_coo_to_device_group (spmv_sparseP/pytorch_api.cpp:184-229).
+ *
+ * n_sp sparse parts (the col_split of spmm.py:127-136) share nrows[0] rows; part i has ncols[i]
+ * columns and nnz[i] nonzeros.  rowidx[i] is the CSR row pointer (nrows[i]+1 int32) or the COO row
+ * index (nnz[i] int32, row-major sorted and coalesced as spmm.py:40-42 produces); colind[i] is
+ * int32[nnz[i]]; values[i] has nnz[i] elements of `dtype`.  dense_cols[n_ds] are the widths of the
+ * dense column parts (dense_split, spmm.py:9-13); they must sum to h_size.
+ *
+ * mem == PYGIM_MEM_HOST: arrays are copied to the device once, here (the reference uploads the
+ * sparse parts once in copy_sparse_*).  mem == PYGIM_MEM_DEVICE: device arrays are BORROWED - the
+ * caller keeps them alive until pygim_spmm_free_group (the reference borrows data_ptr()s the same
+ * way, pytorch_api.cpp:230-232).
+ *
+ * The plan also holds the GPU analogue of the reference's two-level balancing
+ * (support/partition.c:14-317): long rows are cut into nnz-bounded segments so that no warp
+ * owns more than seg_len nonzeros. */
+PYGIM_API int pygim_spmm_to_device_group(int format, int dtype, int n_sp, const int32_t *const *rowidx,
+                               const int32_t *const *colind, const void *const *values, const int64_t *nrows,
+                               const int64_t *ncols, const int64_t *nnz, int n_ds, const int64_t *dense_cols,
+                               int64_t h_size, int mem, pygim_handle_t *out_handle);
+
+/* spmm_free_group (spmm_default/pytorch_api.cpp:198-201; never called by the reference's Python) */
+PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle);
+
+/* plan options: key in {"seg_len", "l2_persist", "chunk_nnz", "block_threads"}; value < 0 = automatic */
+PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int64_t value);
+
+/* Graph statistics the retargeted autotuner consumes (the role of pim_ops.prepare_tune_csr,
+ * utils/autotuner.py:295-302,351): out[0..7] = nrows, ncols, nnz, max row nnz, number of long
+ * rows (cut into segments), number of segments, seg_len, empty rows - for sparse part `part`. */
+PYGIM_API int pygim_plan_stats(pygim_handle_t handle, int part, int64_t *out8);
+
+/* ---------------------------------------------------------------- run ("run_group")
+ * Replaces spmm_csr_run_group / spmm_coo_run_group / spmv_coo_run_group
+ *   spmm_default/pytorch_api.cpp:248-280, :332-367 -> spmm_pim_csr (spmm_mul_csr.c:335-561),
+ *   spmm_pim_coo (spmm_mul_coo.c:323-592); spmv_sparseP/pytorch_api.cpp:231-266.
+ * Semantics (ops.hpp:42-62): C[total_rows x h_size] = sum_i concat_j A_i * B_j[rows_i, :], where
+ * rows_i is the row block of B matching sparse part i's columns.  B_parts[j] is [sum_i ncols[i] x
+ * dense_cols[j]] with row stride ldb[j] (elements); C has row stride ldc (elements).
+ *
+ * _host: B_parts and C are host buffers (pinned buffers transfer at full PCIe rate); the call
+ *        uploads B, runs, downloads C and returns when C is complete - the reference's
+ *        load_dense / kernel / retrieve_result / alignment phases.
+ * _device: B_parts and C are device buffers; work is enqueued on `stream` (a cudaStream_t, NULL =
+ *        legacy default stream) and the call returns without synchronising. */
+PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
+                              void *C, int64_t ldc);
+PYGIM_API int pygim_spmm_run_group_device(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
+                                void *C, int64_t ldc, void *stream);
+
+/* Same computation when the caller already has B as ONE [sum ncols x h_size] device matrix (no
+ * dense_split copies): the dense column parts become column tiles of B/C. */
+PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ldb, void *C, int64_t ldc, void *stream);
+
+/* The five phase timers the reference prints as [DATA]load_sparse_time / load_dense_time /
+ * kernel_time / retrieve_result_time / alignment_time (spmm_mul_csr.c:563-580), in ms, for the
+ * last pygim_spmm_run_group_host call on this handle (alignment is always 0: the kernels write C
+ * in place, there is no host merge). */
+PYGIM_API int pygim_last_timers(pygim_handle_t handle, double *out5_ms);
+
+/* number of kernel launches issued by the last run call on this handle */
+PYGIM_API int pygim_last_launches(pygim_handle_t handle, int64_t *out);
+
+/* ---------------------------------------------------------------- partitioners (host, no GPU needed)
+ * GPU-level analogue of partition_by_nnz_csr (support/partition.c:51-99): cut [0, nrows) into
+ * nparts contiguous row ranges of near-equal nnz.  Unlike the reference's greedy sweep the cut for
+ * part p is the first row whose prefix nnz reaches p*nnz/nparts, so no part is left empty while
+ * rows remain.  split_out has nparts+1 entries. */
+PYGIM_API int pygim_partition_rows_by_nnz(const int32_t *rowptr, int64_t nrows, int nparts, int64_t *split_out);
+/* partition_by_row_csr (support/partition.c:14-44): nrows/nparts rows each, first nrows%nparts get +1 */
+PYGIM_API int pygim_partition_rows_even(int64_t nrows, int nparts, int64_t *split_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYGIM_B200_H */

@@ -1,0 +1,2 @@
+/* TEST INFRASTRUCTURE ONLY: see dpu.h in this directory. */
+#include "dpu.h"

@@ -1,0 +1,152 @@
+"""Shared machinery of the three backend front-ends (spmm / grande / spmv).
+
+Each front-end of the reference is a self-contained copy of the same class
+(backend_pim/spmm.py:15-136, grande.py:25-121, spmv.py:21-109).  Here the common behaviour lives
+once: splitting the adjacency by columns, turning each part into int32 CSR or coalesced COO index
+arrays of the requested value dtype, and holding the plan handle.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import pim_ops
+
+TORCH_TYPES = {"INT64": torch.int64, "INT32": torch.int32, "INT16": torch.int16, "INT8": torch.int8,
+               "FLT32": torch.float32, "DBL64": torch.float64}
+
+
+class _Csr:
+    """The three arrays of one CSR part, with the accessor names of torch.sparse_csr_tensor."""
+
+    def __init__(self, rowptr, col, value, shape):
+        self._rowptr, self._col, self._value, self._shape = rowptr, col, value, tuple(shape)
+
+    def crow_indices(self):
+        return self._rowptr
+
+    def col_indices(self):
+        return self._col
+
+    def values(self):
+        return self._value
+
+    def size(self, dim=None):
+        return self._shape if dim is None else self._shape[dim]
+
+
+class _Coo:
+    """Row-major sorted, duplicate-free COO part (what `.coalesce()` yields, spmm.py:40-42)."""
+
+    def __init__(self, row, col, value, shape):
+        self._row, self._col, self._value, self._shape = row, col, value, tuple(shape)
+
+    def indices(self):
+        return torch.stack([self._row, self._col], dim=0)
+
+    def row_indices(self):
+        return self._row
+
+    def col_indices(self):
+        return self._col
+
+    def values(self):
+        return self._value
+
+    def size(self, dim=None):
+        return self._shape if dim is None else self._shape[dim]
+
+
+def edge_values(item, dtype: torch.dtype) -> torch.Tensor:
+    """Missing edge values become ones, present ones are cast with .type(dtype) (spmm.py:36-39,48-51)."""
+    value = item.coo()[2]
+    if value is None:
+        return torch.ones(item.nnz(), dtype=dtype, device=item.device())
+    return value.type(dtype)
+
+
+def coalesce(row: torch.Tensor, col: torch.Tensor, value: torch.Tensor, ncols: int
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Sort row-major and sum duplicate (row, col) entries in the value dtype (wrapping for ints),
+    i.e. torch.sparse_coo_tensor(...).coalesce() without building a sparse tensor."""
+    if row.numel() == 0:
+        return row, col, value
+    key = row.to(torch.int64) * max(int(ncols), 1) + col.to(torch.int64)
+    if bool((key[1:] > key[:-1]).all()):
+        return row, col, value           # already sorted and unique
+    key, perm = torch.sort(key, stable=True)
+    value = value[perm]
+    uniq, inverse = torch.unique_consecutive(key, return_inverse=True)
+    if uniq.numel() != key.numel():
+        summed = torch.zeros(uniq.numel(), dtype=value.dtype, device=value.device)
+        summed.index_add_(0, inverse, value)
+        value = summed
+    return uniq // max(int(ncols), 1), uniq % max(int(ncols), 1), value
+
+
+def split_widths(total: int, nparts: int) -> List[int]:
+    """ceil(total/nparts) each, remainder in the last part (spmm.py:60-72, :129-133)."""
+    width = (total + nparts - 1) // nparts
+    out = [width] * nparts
+    if nparts * width != total:
+        out[nparts - 1] = total - (nparts - 1) * width
+    return out
+
+
+class SparseTensorBase:
+    """State shared by the front-ends; attribute names follow the reference so callers that read
+    `.dtype`, `.raw`, `.parts`, `.format`, `.hidden_size`, `.dense_parts`, `.sp_info_ptr` keep working
+    (models/pyg_gcn_conv.py:131 reads `.dtype`)."""
+
+    def __init__(self, coo, dtype=torch.int32, format=""):
+        self.raw = coo
+        self.dtype = dtype
+        self.sp_info_ptr: Optional[int] = None
+        self.result = None
+        self.parts = [self.raw]
+        self.dense_parts = 0
+        self.csr: list = []
+        self.coo: list = []
+        self.hidden_size = 0
+        self.nparts = 1
+        self.format = format
+
+    # -- column split of the adjacency (sparse parts; partial products are summed)
+    def col_split(self, nparts=4):
+        assert nparts > 0
+        width = (self.raw.size(1) + nparts - 1) // nparts
+        if nparts != len(self.parts):
+            assert len(self.parts) == 1
+            pieces = [self.raw[:, k * width:(k + 1) * width] for k in range(nparts - 1)]
+            pieces.append(self.raw[:, (nparts - 1) * width:])
+            self.parts = pieces
+            self.csr, self.coo = [], []
+        return self.parts
+
+    def row_split(self, nparts=4):
+        assert False   # spmm.py:124-125
+
+    # -- per-part index arrays
+    def build_csr(self):
+        self.csr = []
+        for item in self.parts:
+            rowptr, col, _ = item.csr()
+            self.csr.append(_Csr(rowptr.int().contiguous(), col.int().contiguous(),
+                                 edge_values(item, self.dtype).contiguous(), item.sizes()[:2]))
+
+    def build_coo(self, pad_to: int = 1):
+        self.coo = []
+        for item in self.parts:
+            row, col, _ = item.coo()
+            n, m = item.size(0), item.size(1)
+            if pad_to > 1 and n % pad_to != 0:     # spmv.py:45-51: BOTH dims grow by the row padding
+                pad = pad_to - n % pad_to
+                n, m = n + pad, m + pad
+            row, col, value = coalesce(row, col, edge_values(item, self.dtype), m)
+            self.coo.append(_Coo(row.int().contiguous(), col.int().contiguous(), value.contiguous(), (n, m)))
+
+    def free(self):
+        if self.sp_info_ptr is not None:
+            pim_ops.spmm_free_group(self.sp_info_ptr)
+            self.sp_info_ptr = None

@@ -1,0 +1,629 @@
+// libbackend_pim.so - C ABI (include/pygim_b200.h), device context and plans.
+//
+// Host-side counterpart of the reference's op layer (spmm_default/pytorch_api.cpp, ops.hpp,
+// spmm_mul_csr.c, spmm_mul_coo.c): bring-up, one-time sparse upload + partition plan
+// ("to_device_group"), and the per-call run ("run_group").  There is no CPU fallback: without a
+// CUDA device every entry point that would compute returns PYGIM_ERR_NO_DEVICE.
+#include "../../include/pygim_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+#include "spmm_csr.cuh"   // struct Seg
+
+namespace pygim {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(PYGIM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static size_t dtype_size(int dt) {
+    switch (dt) {
+        case PYGIM_INT8: return 1;
+        case PYGIM_INT16: return 2;
+        case PYGIM_INT32: return 4;
+        case PYGIM_INT64: return 8;
+        case PYGIM_FLT32: return 4;
+        case PYGIM_DBL64: return 8;
+        default: return 0;
+    }
+}
+
+// ------------------------------------------------------------------------------ device context
+struct Context {
+    bool initialised = false;
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    int max_threads_per_sm = 2048;
+    long long l2_bytes = 0, persisting_max = 0, hbm_bytes = 0;
+    long long nr_ranks = 0, groups_per_rank = 1, nr_dpus = 0;
+    std::mutex mu;
+};
+static Context g_ctx;
+
+static int context_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(PYGIM_ERR_NO_DEVICE,
+                    "no CUDA device visible (%s); pygim_b200 has no CPU fallback", cudaGetErrorString(e));
+    }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) return fail(PYGIM_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    g_ctx.device = device;
+    g_ctx.sm_count = p.multiProcessorCount;
+    g_ctx.cc_major = p.major;
+    g_ctx.cc_minor = p.minor;
+    g_ctx.max_threads_per_sm = p.maxThreadsPerMultiProcessor;
+    g_ctx.l2_bytes = p.l2CacheSize;
+    g_ctx.persisting_max = p.persistingL2CacheMaxSize;
+    g_ctx.hbm_bytes = (long long)p.totalGlobalMem;
+    g_ctx.initialised = true;
+    return PYGIM_OK;
+}
+
+// ------------------------------------------------------------------------------ plans
+struct SparsePart {
+    long long nrows = 0, ncols = 0, nnz = 0;
+    const int *rowidx = nullptr;   // CSR rowptr [nrows+1] or COO rowind [nnz]
+    const int *colind = nullptr;
+    const void *values = nullptr;
+    bool owned = false;            // true: uploaded by us, freed in free_group
+    // CSR second-level balancing (built from rowptr on the host)
+    std::vector<int> h_rowptr;     // host copy (kept for re-planning when seg_len changes)
+    Seg *d_segs = nullptr;
+    int *d_long_rows = nullptr;
+    int *d_long_seg_ptr = nullptr;
+    int n_seg = 0, n_long = 0, seg_len = 0;
+    long long max_row_nnz = 0, empty_rows = 0;
+};
+
+struct Group {
+    int format = PYGIM_CSR;
+    int dtype = PYGIM_FLT32;
+    int device = 0;
+    long long h_size = 0, total_rows = 0, total_cols = 0;
+    std::vector<SparsePart> parts;
+    std::vector<long long> dense_cols;
+    // options (< 0 = automatic)
+    long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1;
+    // scratch
+    void *d_partial = nullptr;
+    size_t partial_bytes = 0;
+    void *d_B = nullptr;   // staging for the host entry point
+    void *d_C = nullptr;
+    size_t dB_bytes = 0, dC_bytes = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double timers_ms[5] = {0, 0, 0, 0, 0};
+    int64_t last_launches = 0;
+};
+
+static int auto_seg_len(const SparsePart &p) {
+    // ~8 items per resident warp, 256..4096 nonzeros per item
+    const long long slots = (long long)g_ctx.sm_count * (g_ctx.max_threads_per_sm / 32);
+    long long s = p.nnz / std::max<long long>(1, slots * 8);
+    long long pow2 = 256;
+    while (pow2 < s && pow2 < 4096) pow2 <<= 1;
+    return (int)pow2;
+}
+
+static void free_csr_plan(SparsePart &p) {
+    if (p.d_segs) cudaFree(p.d_segs);
+    if (p.d_long_rows) cudaFree(p.d_long_rows);
+    if (p.d_long_seg_ptr) cudaFree(p.d_long_seg_ptr);
+    p.d_segs = nullptr;
+    p.d_long_rows = nullptr;
+    p.d_long_seg_ptr = nullptr;
+    p.n_seg = p.n_long = 0;
+}
+
+// Cut every row longer than seg_len into ceil(nnz/seg_len) near-equal segments.
+static int build_csr_plan(SparsePart &p, int seg_len) {
+    free_csr_plan(p);
+    p.seg_len = seg_len;
+    std::vector<Seg> segs;
+    std::vector<int> long_rows, long_ptr;
+    long_ptr.push_back(0);
+    p.max_row_nnz = 0;
+    p.empty_rows = 0;
+    const std::vector<int> &rp = p.h_rowptr;
+    for (long long r = 0; r < p.nrows; ++r) {
+        const long long s = (unsigned)rp[r], e = (unsigned)rp[r + 1];
+        const long long n = e - s;
+        if (n > p.max_row_nnz) p.max_row_nnz = n;
+        if (n == 0) ++p.empty_rows;
+        if (n > seg_len) {
+            const long long k = (n + seg_len - 1) / seg_len;
+            // equal pieces rounded up to a multiple of 32 so every piece but the last runs full batches
+            long long piece = ((n + k - 1) / k + 31) / 32 * 32;
+            for (long long b = s; b < e; b += piece) {
+                Seg sg;
+                sg.row = (int)r;
+                sg.start = (int)b;
+                sg.end = (int)std::min(e, b + piece);
+                sg.slot = (int)segs.size();
+                segs.push_back(sg);
+            }
+            long_rows.push_back((int)r);
+            long_ptr.push_back((int)segs.size());
+        }
+    }
+    p.n_seg = (int)segs.size();
+    p.n_long = (int)long_rows.size();
+    if (p.n_seg > 0) {
+        // longest pieces first: the block scheduler hands out blocks in index order
+        std::stable_sort(segs.begin(), segs.end(),
+                         [](const Seg &x, const Seg &y) { return (x.end - x.start) > (y.end - y.start); });
+        CUDA_TRY(cudaMalloc(&p.d_segs, segs.size() * sizeof(Seg)));
+        CUDA_TRY(cudaMemcpy(p.d_segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&p.d_long_rows, long_rows.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(p.d_long_rows, long_rows.data(), long_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&p.d_long_seg_ptr, long_ptr.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(p.d_long_seg_ptr, long_ptr.data(), long_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return PYGIM_OK;
+}
+
+static Group *as_group(pygim_handle_t h) { return reinterpret_cast<Group *>(static_cast<uintptr_t>(h)); }
+
+static void destroy_group(Group *g) {
+    if (!g) return;
+    for (auto &p : g->parts) {
+        free_csr_plan(p);
+        if (p.owned) {
+            cudaFree(const_cast<int *>(p.rowidx));
+            cudaFree(const_cast<int *>(p.colind));
+            cudaFree(const_cast<void *>(p.values));
+        }
+    }
+    if (g->d_partial) cudaFree(g->d_partial);
+    if (g->d_B) cudaFree(g->d_B);
+    if (g->d_C) cudaFree(g->d_C);
+    for (auto &e : g->ev)
+        if (e) cudaEventDestroy(e);
+    delete g;
+}
+
+template <typename L> static cudaError_t dispatch_csr(int dtype, const L &l, int64_t *n) {
+    switch (dtype) {
+        case PYGIM_INT8: return launch_csr_i8(l, n);
+        case PYGIM_INT16: return launch_csr_i16(l, n);
+        case PYGIM_INT32: return launch_csr_i32(l, n);
+        case PYGIM_INT64: return launch_csr_i64(l, n);
+        case PYGIM_FLT32: return launch_csr_f32(l, n);
+        default: return launch_csr_f64(l, n);
+    }
+}
+template <typename L> static cudaError_t dispatch_coo(int dtype, const L &l, int64_t *n) {
+    switch (dtype) {
+        case PYGIM_INT8: return launch_coo_i8(l, n);
+        case PYGIM_INT16: return launch_coo_i16(l, n);
+        case PYGIM_INT32: return launch_coo_i32(l, n);
+        case PYGIM_INT64: return launch_coo_i64(l, n);
+        case PYGIM_FLT32: return launch_coo_f32(l, n);
+        default: return launch_coo_f64(l, n);
+    }
+}
+
+// C[:, col0:col0+w] (+)= A_i * B_tile[rows_i, :]  for one (sparse part, dense tile)
+static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char *C, long long ldc, long long width,
+                    bool accumulate, cudaStream_t stream) {
+    const size_t s = dtype_size(g->dtype);
+    cudaError_t err;
+    if (g->format == PYGIM_CSR) {
+        long long ldp = (width * (long long)s + 15) / 16 * 16 / (long long)s;
+        if (p.n_seg > 0) {
+            const size_t need = (size_t)p.n_seg * (size_t)ldp * s;
+            if (need > g->partial_bytes) {
+                // grow-only scratch; stream-ordered free keeps earlier launches valid
+                if (g->d_partial) CUDA_TRY(cudaFreeAsync(g->d_partial, stream));
+                CUDA_TRY(cudaMallocAsync(&g->d_partial, need, stream));
+                g->partial_bytes = need;
+            }
+        }
+        CsrLaunch l;
+        l.rowptr = p.rowidx;
+        l.colind = p.colind;
+        l.val = p.values;
+        l.B = B;
+        l.C = C;
+        l.partial = g->d_partial;
+        l.segs = p.d_segs;
+        l.long_rows = p.d_long_rows;
+        l.long_seg_ptr = p.d_long_seg_ptr;
+        l.n_seg = p.n_seg;
+        l.n_long = p.n_long;
+        l.nrows = (int)p.nrows;
+        l.seg_len = p.seg_len;
+        l.ncols = width;
+        l.ldb = ldb;
+        l.ldc = ldc;
+        l.ldp = ldp;
+        l.accumulate = accumulate ? 1 : 0;
+        l.stream = stream;
+        err = dispatch_csr(g->dtype, l, &g->last_launches);
+    } else {
+        CooLaunch l;
+        l.rowind = p.rowidx;
+        l.colind = p.colind;
+        l.val = p.values;
+        l.B = B;
+        l.C = C;
+        l.nnz = p.nnz;
+        l.nrows = p.nrows;
+        l.ncols = width;
+        l.ldb = ldb;
+        l.ldc = ldc;
+        l.chunk_nnz = (int)g->opt_chunk_nnz;
+        l.accumulate = accumulate ? 1 : 0;
+        l.n_warp_slots = g_ctx.sm_count * (g_ctx.max_threads_per_sm / 32);
+        l.stream = stream;
+        err = dispatch_coo(g->dtype, l, &g->last_launches);
+    }
+    if (err != cudaSuccess) return fail(PYGIM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    return PYGIM_OK;
+}
+
+// The (sparse part x dense part) loop of spmm_pim_csr / spmm_host_*_group (ops.hpp:42-62):
+// dense part j of width h_j lands at column offset sum_{k<j} h_k; sparse part 0 overwrites, parts >= 1 add.
+static int run_group_device(Group *g, int n_ds, const void *const *B_parts, const long long *ldb, void *C,
+                            long long ldc, cudaStream_t stream) {
+    if (n_ds != (int)g->dense_cols.size())
+        return fail(PYGIM_ERR_INVALID, "expected %d dense parts, got %d", (int)g->dense_cols.size(), n_ds);
+    const size_t s = dtype_size(g->dtype);
+    g->last_launches = 0;
+    long long brow = 0;
+    for (size_t i = 0; i < g->parts.size(); ++i) {
+        long long ccol = 0;
+        for (int j = 0; j < n_ds; ++j) {
+            const long long w = g->dense_cols[j];
+            const char *B = static_cast<const char *>(B_parts[j]) + (size_t)brow * (size_t)ldb[j] * s;
+            char *Ct = static_cast<char *>(C) + (size_t)ccol * s;
+            int rc = run_tile(g, g->parts[i], B, ldb[j], Ct, ldc, w, i > 0, stream);
+            if (rc) return rc;
+            ccol += w;
+        }
+        brow += g->parts[i].ncols;
+    }
+    return PYGIM_OK;
+}
+
+}  // namespace pygim
+
+using namespace pygim;
+
+// =============================================================================== C ABI
+extern "C" {
+
+PYGIM_API const char *pygim_last_error(void) { return g_err.c_str(); }
+PYGIM_API int pygim_abi_version(void) { return 1; }
+
+PYGIM_API int pygim_dpu_init_ranks(int64_t nr_ranks, int64_t groups_per_rank, int device, int32_t *units_per_rank_out) {
+    if (nr_ranks <= 0) return fail(PYGIM_ERR_INVALID, "nr_ranks must be positive, got %lld", (long long)nr_ranks);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    int rc = context_init(device);
+    if (rc) return rc;
+    g_ctx.nr_ranks = nr_ranks;
+    g_ctx.groups_per_rank = groups_per_rank > 0 ? groups_per_rank : 1;
+    g_ctx.nr_dpus = 0;
+    if (units_per_rank_out) {
+        const int per = std::max<long long>(1, g_ctx.sm_count / nr_ranks);
+        for (int64_t i = 0; i < nr_ranks; ++i) units_per_rank_out[i] = per;
+    }
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_dpu_init_dpus(int64_t nr_dpus, int device) {
+    if (nr_dpus <= 0) return fail(PYGIM_ERR_INVALID, "nr_dpus must be positive, got %lld", (long long)nr_dpus);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    int rc = context_init(device);
+    if (rc) return rc;
+    g_ctx.nr_dpus = nr_dpus;
+    g_ctx.nr_ranks = 1;
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_dpu_release(void) {
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    g_ctx.initialised = false;
+    g_ctx.nr_ranks = g_ctx.nr_dpus = 0;
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_device_info(int *device, int *sm_count, int64_t *l2_bytes, int64_t *persisting_l2_max_bytes,
+                      int64_t *hbm_bytes, int *cc_major, int *cc_minor) {
+    if (!g_ctx.initialised) return fail(PYGIM_ERR_NOT_INIT, "call pygim_dpu_init_ranks / pygim_dpu_init_dpus first");
+    if (device) *device = g_ctx.device;
+    if (sm_count) *sm_count = g_ctx.sm_count;
+    if (l2_bytes) *l2_bytes = g_ctx.l2_bytes;
+    if (persisting_l2_max_bytes) *persisting_l2_max_bytes = g_ctx.persisting_max;
+    if (hbm_bytes) *hbm_bytes = g_ctx.hbm_bytes;
+    if (cc_major) *cc_major = g_ctx.cc_major;
+    if (cc_minor) *cc_minor = g_ctx.cc_minor;
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_spmm_to_device_group(int format, int dtype, int n_sp, const int32_t *const *rowidx,
+                               const int32_t *const *colind, const void *const *values, const int64_t *nrows,
+                               const int64_t *ncols, const int64_t *nnz, int n_ds, const int64_t *dense_cols,
+                               int64_t h_size, int mem, pygim_handle_t *out_handle) {
+    if (!out_handle) return fail(PYGIM_ERR_INVALID, "out_handle is NULL");
+    *out_handle = 0;
+    if (!g_ctx.initialised) return fail(PYGIM_ERR_NOT_INIT, "call pygim_dpu_init_ranks / pygim_dpu_init_dpus first");
+    if (format != PYGIM_CSR && format != PYGIM_COO) return fail(PYGIM_ERR_INVALID, "unknown format %d", format);
+    const size_t s = dtype_size(dtype);
+    if (s == 0) return fail(PYGIM_ERR_INVALID, "unknown dtype %d", dtype);
+    if (n_sp <= 0 || n_ds <= 0) return fail(PYGIM_ERR_INVALID, "need at least one sparse and one dense part");
+    if (mem != PYGIM_MEM_HOST && mem != PYGIM_MEM_DEVICE) return fail(PYGIM_ERR_INVALID, "unknown mem kind %d", mem);
+    long long hsum = 0;
+    for (int j = 0; j < n_ds; ++j) {
+        if (dense_cols[j] < 0) return fail(PYGIM_ERR_INVALID, "negative dense part width");
+        hsum += dense_cols[j];
+    }
+    if (hsum != h_size)   // the reference assert()s this at run time (pytorch_api.cpp:266)
+        return fail(PYGIM_ERR_INVALID, "dense part widths sum to %lld, h_size is %lld", hsum, (long long)h_size);
+    for (int i = 0; i < n_sp; ++i) {
+        if (nrows[i] != nrows[0]) return fail(PYGIM_ERR_INVALID, "sparse parts must share the row count (col_split)");
+        if (nrows[i] < 0 || ncols[i] < 0 || nnz[i] < 0 || nnz[i] > 0x7fffffffLL || nrows[i] >= 0x7fffffffLL)
+            return fail(PYGIM_ERR_INVALID, "sparse part %d: sizes out of the int32 index range", i);
+    }
+    CUDA_TRY(cudaSetDevice(g_ctx.device));
+
+    Group *g = new Group;
+    g->format = format;
+    g->dtype = dtype;
+    g->device = g_ctx.device;
+    g->h_size = h_size;
+    g->total_rows = nrows[0];
+    g->dense_cols.assign(dense_cols, dense_cols + n_ds);
+    g->parts.resize(n_sp);
+    auto bail = [&](int rc) { destroy_group(g); return rc; };
+
+    for (int i = 0; i < n_sp; ++i) {
+        SparsePart &p = g->parts[i];
+        p.nrows = nrows[i];
+        p.ncols = ncols[i];
+        p.nnz = nnz[i];
+        g->total_cols += ncols[i];
+        const size_t ridx_n = format == PYGIM_CSR ? (size_t)nrows[i] + 1 : (size_t)nnz[i];
+        if (mem == PYGIM_MEM_HOST) {
+            int *d_r = nullptr, *d_c = nullptr;
+            void *d_v = nullptr;
+            p.owned = true;
+            cudaError_t e;
+            if ((e = cudaMalloc(&d_r, std::max<size_t>(ridx_n, 1) * 4)) != cudaSuccess ||
+                (e = cudaMalloc(&d_c, std::max<size_t>((size_t)nnz[i], 1) * 4)) != cudaSuccess ||
+                (e = cudaMalloc(&d_v, std::max<size_t>((size_t)nnz[i], 1) * s)) != cudaSuccess) {
+                p.rowidx = d_r; p.colind = d_c; p.values = d_v;
+                return bail(fail(PYGIM_ERR_CUDA, "cudaMalloc of sparse part %d failed: %s", i, cudaGetErrorString(e)));
+            }
+            p.rowidx = d_r; p.colind = d_c; p.values = d_v;
+            if ((e = cudaMemcpy(d_r, rowidx[i], ridx_n * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMemcpy(d_c, colind[i], (size_t)nnz[i] * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMemcpy(d_v, values[i], (size_t)nnz[i] * s, cudaMemcpyHostToDevice)) != cudaSuccess)
+                return bail(fail(PYGIM_ERR_CUDA, "upload of sparse part %d failed: %s", i, cudaGetErrorString(e)));
+        } else {
+            p.owned = false;
+            p.rowidx = rowidx[i];
+            p.colind = colind[i];
+            p.values = values[i];
+        }
+        if (format == PYGIM_CSR) {
+            p.h_rowptr.resize((size_t)nrows[i] + 1);
+            if (mem == PYGIM_MEM_HOST) {
+                std::memcpy(p.h_rowptr.data(), rowidx[i], ((size_t)nrows[i] + 1) * 4);
+            } else {
+                cudaError_t e = cudaMemcpy(p.h_rowptr.data(), rowidx[i], ((size_t)nrows[i] + 1) * 4, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess)
+                    return bail(fail(PYGIM_ERR_CUDA, "read-back of rowptr failed: %s", cudaGetErrorString(e)));
+            }
+            if ((long long)(unsigned)p.h_rowptr[(size_t)nrows[i]] != nnz[i] || p.h_rowptr[0] != 0)
+                return bail(fail(PYGIM_ERR_INVALID, "sparse part %d: rowptr does not span [0, nnz]", i));
+            int rc = build_csr_plan(p, auto_seg_len(p));
+            if (rc) return bail(rc);
+        }
+    }
+    for (auto &e : g->ev) {
+        cudaError_t ce = cudaEventCreate(&e);
+        if (ce != cudaSuccess) return bail(fail(PYGIM_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(ce)));
+    }
+    *out_handle = static_cast<pygim_handle_t>(reinterpret_cast<uintptr_t>(g));
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle) {
+    Group *g = as_group(handle);
+    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    destroy_group(g);
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int64_t value) {
+    Group *g = as_group(handle);
+    if (!g || !key) return fail(PYGIM_ERR_INVALID, "null handle or key");
+    if (!std::strcmp(key, "seg_len")) {
+        g->opt_seg_len = value;
+        if (g->format == PYGIM_CSR) {
+            CUDA_TRY(cudaSetDevice(g->device));
+            CUDA_TRY(cudaDeviceSynchronize());
+            for (auto &p : g->parts) {
+                int rc = build_csr_plan(p, value > 0 ? (int)std::min<int64_t>(value, 1 << 30) : auto_seg_len(p));
+                if (rc) return rc;
+            }
+        }
+    } else if (!std::strcmp(key, "l2_persist")) {
+        g->opt_l2_persist = value;
+    } else if (!std::strcmp(key, "chunk_nnz")) {
+        g->opt_chunk_nnz = value;
+    } else {
+        return fail(PYGIM_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_plan_stats(pygim_handle_t handle, int part, int64_t *out8) {
+    Group *g = as_group(handle);
+    if (!g || !out8) return fail(PYGIM_ERR_INVALID, "null handle or output");
+    if (part < 0 || part >= (int)g->parts.size()) return fail(PYGIM_ERR_INVALID, "part %d out of range", part);
+    const SparsePart &p = g->parts[part];
+    out8[0] = p.nrows;
+    out8[1] = p.ncols;
+    out8[2] = p.nnz;
+    out8[3] = p.max_row_nnz;
+    out8[4] = p.n_long;
+    out8[5] = p.n_seg;
+    out8[6] = p.seg_len;
+    out8[7] = p.empty_rows;
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_spmm_run_group_device(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
+                                void *C, int64_t ldc, void *stream) {
+    Group *g = as_group(handle);
+    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    if (!B_parts || !ldb || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
+    std::vector<long long> l(ldb, ldb + n_ds);
+    return run_group_device(g, n_ds, B_parts, l.data(), C, ldc, static_cast<cudaStream_t>(stream));
+}
+
+PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ldb, void *C, int64_t ldc, void *stream) {
+    Group *g = as_group(handle);
+    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    if (!B || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
+    // the dense parts are column tiles of the one B matrix
+    const size_t s = dtype_size(g->dtype);
+    std::vector<const void *> parts(g->dense_cols.size());
+    std::vector<long long> lds(g->dense_cols.size(), ldb);
+    long long col = 0;
+    for (size_t j = 0; j < g->dense_cols.size(); ++j) {
+        parts[j] = static_cast<const char *>(B) + (size_t)col * s;
+        col += g->dense_cols[j];
+    }
+    return run_group_device(g, (int)parts.size(), parts.data(), lds.data(), C, ldc, static_cast<cudaStream_t>(stream));
+}
+
+PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
+                              void *C, int64_t ldc) {
+    Group *g = as_group(handle);
+    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    if (!B_parts || !ldb || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
+    if (n_ds != (int)g->dense_cols.size())
+        return fail(PYGIM_ERR_INVALID, "expected %d dense parts, got %d", (int)g->dense_cols.size(), n_ds);
+    CUDA_TRY(cudaSetDevice(g->device));
+    const size_t s = dtype_size(g->dtype);
+    const size_t rowsB = (size_t)g->total_cols, rowsC = (size_t)g->total_rows, H = (size_t)g->h_size;
+    // device staging: B as one [rowsB x H] matrix (dense parts side by side), C as [rowsC x H]
+    const size_t needB = std::max<size_t>(rowsB * H * s, 16), needC = std::max<size_t>(rowsC * H * s, 16);
+    if (needB > g->dB_bytes) {
+        if (g->d_B) CUDA_TRY(cudaFree(g->d_B));
+        g->d_B = nullptr; g->dB_bytes = 0;
+        CUDA_TRY(cudaMalloc(&g->d_B, needB));
+        g->dB_bytes = needB;
+    }
+    if (needC > g->dC_bytes) {
+        if (g->d_C) CUDA_TRY(cudaFree(g->d_C));
+        g->d_C = nullptr; g->dC_bytes = 0;
+        CUDA_TRY(cudaMalloc(&g->d_C, needC));
+        g->dC_bytes = needC;
+    }
+    cudaStream_t st = cudaStreamPerThread;
+    CUDA_TRY(cudaEventRecord(g->ev[0], st));
+    long long col = 0;
+    for (int j = 0; j < n_ds; ++j) {   // load_dense: the reference's dpu_broadcast_to (spmm_mul_csr.c:352-367)
+        const size_t w = (size_t)g->dense_cols[j];
+        if (w && rowsB)
+            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(g->d_B) + (size_t)col * s, H * s, B_parts[j],
+                                       (size_t)ldb[j] * s, w * s, rowsB, cudaMemcpyHostToDevice, st));
+        col += (long long)w;
+    }
+    CUDA_TRY(cudaEventRecord(g->ev[1], st));
+    int rc = pygim_spmm_device(handle, g->d_B, (int64_t)H, g->d_C, (int64_t)H, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(g->ev[2], st));
+    if (rowsC && H)   // retrieve_result (spmm_mul_csr.c:385-410); no merge step follows
+        CUDA_TRY(cudaMemcpy2DAsync(C, (size_t)ldc * s, g->d_C, H * s, H * s, rowsC, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(g->ev[3], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    g->timers_ms[0] = 0;   // load_sparse: done once in to_device_group
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->timers_ms[1] = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->timers_ms[2] = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[2], g->ev[3])); g->timers_ms[3] = ms;
+    g->timers_ms[4] = 0;   // alignment: none
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_last_timers(pygim_handle_t handle, double *out5_ms) {
+    Group *g = as_group(handle);
+    if (!g || !out5_ms) return fail(PYGIM_ERR_INVALID, "null handle or output");
+    for (int i = 0; i < 5; ++i) out5_ms[i] = g->timers_ms[i];
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_last_launches(pygim_handle_t handle, int64_t *out) {
+    Group *g = as_group(handle);
+    if (!g || !out) return fail(PYGIM_ERR_INVALID, "null handle or output");
+    *out = g->last_launches;
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_partition_rows_by_nnz(const int32_t *rowptr, int64_t nrows, int nparts, int64_t *split_out) {
+    if (!rowptr || !split_out || nparts <= 0 || nrows < 0) return fail(PYGIM_ERR_INVALID, "bad partition arguments");
+    const long long nnz = (unsigned)rowptr[nrows];
+    split_out[0] = 0;
+    long long r = 0;
+    for (int p = 1; p < nparts; ++p) {
+        const long long target = (nnz * p + nparts - 1) / nparts;
+        // first row boundary whose prefix reaches the target
+        const int32_t *it = std::lower_bound(rowptr + r, rowptr + nrows + 1, target,
+                                             [](int32_t a, long long t) { return (long long)(unsigned)a < t; });
+        r = std::min<long long>(it - rowptr, nrows);
+        split_out[p] = r;
+    }
+    split_out[nparts] = nrows;
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_partition_rows_even(int64_t nrows, int nparts, int64_t *split_out) {
+    if (!split_out || nparts <= 0 || nrows < 0) return fail(PYGIM_ERR_INVALID, "bad partition arguments");
+    const long long chunk = nrows / nparts, rest = nrows % nparts;
+    long long cur = 0;
+    split_out[0] = 0;
+    for (int i = 0; i < nparts; ++i) {
+        cur += chunk + (i < rest ? 1 : 0);
+        split_out[i + 1] = cur;
+    }
+    return PYGIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// Instantiates the CSR / COO kernels for ONE element type and provides its launchers.
+// Compiled six times: -DPYGIM_T=int8_t -DPYGIM_SFX=i8, ... (see build.py).
+#include "launch.h"
+#include "spmm_coo.cuh"
+#include "spmm_csr.cuh"
+
+#ifndef PYGIM_T
+#error "compile with -DPYGIM_T=<type> -DPYGIM_SFX=<suffix>"
+#endif
+
+namespace pygim {
+
+#define PYGIM_CAT2(a, b) a##b
+#define PYGIM_CAT(a, b) PYGIM_CAT2(a, b)
+
+using T = PYGIM_T;
+
+static inline int align_bytes(const void *p) { return (int)(reinterpret_cast<uintptr_t>(p) & 15); }
+
+// 16-byte words when every row start is 16-byte aligned, single elements otherwise
+static bool can_vectorize(const void *B, const void *C, long long ncols, long long ldb, long long ldc, long long ldp) {
+    const long long s = (long long)sizeof(T);
+    return align_bytes(B) == 0 && align_bytes(C) == 0 && (ncols * s) % 16 == 0 && (ldb * s) % 16 == 0 &&
+           (ldc * s) % 16 == 0 && (ldp * s) % 16 == 0;
+}
+
+static int pow2_ceil(long long v) {
+    int g = 1;
+    while (g < v && g < 32) g <<= 1;
+    return g;
+}
+
+template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *launches) {
+    CsrArgs<T> a;
+    a.rowptr = l.rowptr;
+    a.colind = l.colind;
+    a.val = static_cast<const T *>(l.val);
+    a.B = static_cast<const T *>(l.B);
+    a.C = static_cast<T *>(l.C);
+    a.partial = static_cast<T *>(l.partial);
+    a.segs = l.segs;
+    a.n_seg = l.n_seg;
+    a.nrows = l.nrows;
+    a.seg_len = l.seg_len;
+    a.nvec = (int)(l.ncols / E);
+    a.ldb = l.ldb;
+    a.ldc = l.ldc;
+    a.ldp = l.ldp;
+    a.accumulate = l.accumulate;
+    const long long items = (long long)l.n_seg + l.nrows;
+    if (items == 0 || a.nvec == 0) return cudaSuccess;
+    const int G = pow2_ceil(a.nvec);
+    dim3 grid((unsigned)((items + kCsrWarpsPerBlock - 1) / kCsrWarpsPerBlock), (unsigned)((a.nvec + G - 1) / G));
+    dim3 block(kCsrWarpsPerBlock * 32);
+    switch (G) {
+        case 1: csr_spmm_kernel<T, E, 1><<<grid, block, 0, l.stream>>>(a); break;
+        case 2: csr_spmm_kernel<T, E, 2><<<grid, block, 0, l.stream>>>(a); break;
+        case 4: csr_spmm_kernel<T, E, 4><<<grid, block, 0, l.stream>>>(a); break;
+        case 8: csr_spmm_kernel<T, E, 8><<<grid, block, 0, l.stream>>>(a); break;
+        case 16: csr_spmm_kernel<T, E, 16><<<grid, block, 0, l.stream>>>(a); break;
+        default: csr_spmm_kernel<T, E, 32><<<grid, block, 0, l.stream>>>(a); break;
+    }
+    ++*launches;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    if (l.n_long > 0) {
+        FixupArgs<T> f;
+        f.partial = a.partial;
+        f.C = a.C;
+        f.long_rows = l.long_rows;
+        f.long_seg_ptr = l.long_seg_ptr;
+        f.ldp = l.ldp;
+        f.ldc = l.ldc;
+        f.ncols = (int)l.ncols;
+        f.accumulate = l.accumulate;
+        const int threads = l.ncols >= 128 ? 128 : (l.ncols > 32 ? 64 : 32);
+        csr_fixup_kernel<T><<<l.n_long, threads, 0, l.stream>>>(f);
+        ++*launches;
+        err = cudaGetLastError();
+    }
+    return err;
+}
+
+cudaError_t PYGIM_CAT(launch_csr_, PYGIM_SFX)(const CsrLaunch &l, int64_t *launches) {
+    if (can_vectorize(l.B, l.C, l.ncols, l.ldb, l.ldc, l.ldp)) return launch_csr_e<16 / (int)sizeof(T)>(l, launches);
+    return launch_csr_e<1>(l, launches);
+}
+
+template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *launches) {
+    CooArgs<T> a;
+    a.rowind = l.rowind;
+    a.colind = l.colind;
+    a.val = static_cast<const T *>(l.val);
+    a.B = static_cast<const T *>(l.B);
+    a.C = static_cast<T *>(l.C);
+    a.nnz = l.nnz;
+    a.ldb = l.ldb;
+    a.ldc = l.ldc;
+    a.nvec = (int)(l.ncols / E);
+    a.accumulate = l.accumulate;
+    cudaError_t err;
+    if (!l.accumulate && l.nrows > 0 && l.ncols > 0) {
+        // the reference hands the kernels a torch::zeros result (pytorch_api.cpp:357-358)
+        err = cudaMemset2DAsync(l.C, (size_t)l.ldc * sizeof(T), 0, (size_t)l.ncols * sizeof(T), (size_t)l.nrows,
+                                l.stream);
+        if (err != cudaSuccess) return err;
+        ++*launches;
+    }
+    if (l.nnz == 0 || a.nvec == 0) return cudaSuccess;
+    const int G = pow2_ceil(a.nvec);
+    const int P = 32 / G;
+    // exact equal-nnz chunks (BLNC_NNZ): aim at ~8 chunks per resident warp, 64..2048 nonzeros each
+    long long chunk = l.chunk_nnz;
+    if (chunk <= 0) {
+        chunk = l.nnz / ((long long)(l.n_warp_slots > 0 ? l.n_warp_slots : 9472) * 8);
+        if (chunk < 64) chunk = 64;
+        if (chunk > 2048) chunk = 2048;
+    }
+    long long sub = (chunk + P - 1) / P;
+    sub = (sub + G - 1) / G * G;
+    a.sub_nnz = (int)sub;
+    const long long per_warp = sub * P;
+    const long long warps = (l.nnz + per_warp - 1) / per_warp;
+    dim3 grid((unsigned)((warps + kCooWarpsPerBlock - 1) / kCooWarpsPerBlock), (unsigned)((a.nvec + G - 1) / G));
+    dim3 block(kCooWarpsPerBlock * 32);
+    switch (G) {
+        case 1: coo_spmm_kernel<T, E, 1><<<grid, block, 0, l.stream>>>(a); break;
+        case 2: coo_spmm_kernel<T, E, 2><<<grid, block, 0, l.stream>>>(a); break;
+        case 4: coo_spmm_kernel<T, E, 4><<<grid, block, 0, l.stream>>>(a); break;
+        case 8: coo_spmm_kernel<T, E, 8><<<grid, block, 0, l.stream>>>(a); break;
+        case 16: coo_spmm_kernel<T, E, 16><<<grid, block, 0, l.stream>>>(a); break;
+        default: coo_spmm_kernel<T, E, 32><<<grid, block, 0, l.stream>>>(a); break;
+    }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t PYGIM_CAT(launch_coo_, PYGIM_SFX)(const CooLaunch &l, int64_t *launches) {
+    if (can_vectorize(l.B, l.C, l.ncols, l.ldb, l.ldc, 16)) return launch_coo_e<16 / (int)sizeof(T)>(l, launches);
+    return launch_coo_e<1>(l, launches);
+}
+
+}  // namespace pygim

@@ -1,0 +1,53 @@
+// Type-erased launch descriptors shared by backend_pim.cu (C ABI, plans) and kernels_inst.cu
+// (one translation unit per dtype, compiled with -DPYGIM_T=... -DPYGIM_SFX=...).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pygim {
+
+struct Seg;
+
+struct CsrLaunch {
+    const int *rowptr;
+    const int *colind;
+    const void *val;
+    const void *B;
+    void *C;
+    void *partial;            // scratch [n_seg x ldp]
+    const Seg *segs;
+    const int *long_rows;
+    const int *long_seg_ptr;
+    int n_seg, n_long, nrows, seg_len;
+    long long ncols;          // dense columns of this tile
+    long long ldb, ldc, ldp;  // row strides in elements
+    int accumulate;
+    cudaStream_t stream;
+};
+
+struct CooLaunch {
+    const int *rowind;
+    const int *colind;
+    const void *val;
+    const void *B;
+    void *C;
+    long long nnz, nrows, ncols;
+    long long ldb, ldc;
+    int chunk_nnz;            // target nonzeros per warp; <= 0 = automatic
+    int accumulate;           // 0: the launcher zero-fills the C tile first
+    int n_warp_slots;         // resident warps of the device (for the automatic chunk size)
+    cudaStream_t stream;
+};
+
+#define PYGIM_DECLARE_LAUNCHERS(SFX)                                   \
+    cudaError_t launch_csr_##SFX(const CsrLaunch &l, int64_t *launches); \
+    cudaError_t launch_coo_##SFX(const CooLaunch &l, int64_t *launches);
+
+PYGIM_DECLARE_LAUNCHERS(i8)
+PYGIM_DECLARE_LAUNCHERS(i16)
+PYGIM_DECLARE_LAUNCHERS(i32)
+PYGIM_DECLARE_LAUNCHERS(i64)
+PYGIM_DECLARE_LAUNCHERS(f32)
+PYGIM_DECLARE_LAUNCHERS(f64)
+
+}  // namespace pygim

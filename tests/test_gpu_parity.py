@@ -1,0 +1,107 @@
+"""GPU parity: the sm_100a kernels behind the backend_pim API vs the CPU oracle, bit-exact for integers
+and for integer-valued floats (the reference's own inputs), within the stated tolerance otherwise."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ALL_DTYPES, NP_DTYPES, features, make_args, oracle_spmm, random_adj
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(front, adj, args, x, **kw):
+    if front == "spmm":
+        from pygim_b200.backend_pim.spmm import prepare_pim_spmm
+        A = prepare_pim_spmm(adj, args)
+    elif front == "grande":
+        from pygim_b200.backend_pim.grande import prepare_pim_spmm_grande
+        A = prepare_pim_spmm_grande(adj, args, kw["dpus_per_rank"])
+    else:
+        from pygim_b200.backend_pim.spmv import prepare_pim_spmv
+        A = prepare_pim_spmv(adj, args)
+    out = A.mul(x)
+    if out.is_cuda:
+        torch.cuda.synchronize()
+    A.free()
+    return out
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+@pytest.mark.parametrize("hidden", [1, 3, 16, 32, 33, 64, 128, 256])
+def test_spmm_all_dtypes_host_operand(gpu_backend, oracle, dtype, fmt, hidden):
+    adj = random_adj(301, 301, 0.05, seed=hidden, empty_rows=(0, 7, 300), long_row=5)
+    x = features(301, hidden, dtype, seed=1)
+    out = _run("spmm", adj, make_args(dtype, fmt, hidden), x)
+    assert out.dtype == dtype and out.device.type == "cpu"
+    assert torch.equal(out, oracle_spmm(oracle, adj, x, dtype))
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+def test_spmm_device_operand_with_values(gpu_backend, oracle, dtype, fmt):
+    adj = random_adj(500, 500, 0.04, seed=3, value_dtype=dtype, long_row=11)
+    x = features(500, 64, dtype, seed=2)
+    out = _run("spmm", adj.to("cuda"), make_args(dtype, fmt, 64), x.cuda())
+    assert out.is_cuda
+    assert torch.equal(out.cpu(), oracle_spmm(oracle, adj, x, dtype))
+
+
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+@pytest.mark.parametrize("sp_parts,ds_parts", [(1, 1), (2, 1), (1, 2), (3, 4), (4, 3), (7, 5)])
+def test_sp_ds_partitioning(gpu_backend, oracle, fmt, sp_parts, ds_parts):
+    for dtype in (torch.int32, torch.float32, torch.int8):
+        adj = random_adj(257, 257, 0.06, seed=5, value_dtype=dtype)
+        x = features(257, 40, dtype, seed=4)
+        out = _run("spmm", adj, make_args(dtype, fmt, 40, sp_parts, ds_parts), x)
+        assert torch.equal(out, oracle_spmm(oracle, adj, x, dtype)), (dtype, sp_parts, ds_parts)
+
+
+def test_int8_overflow_wraps(gpu_backend, oracle):
+    adj = random_adj(64, 64, 0.9, seed=9, value_dtype=torch.int8, value_range=(-128, 128))
+    x = torch.randint(-128, 128, (64, 32), dtype=torch.int32).to(torch.int8)
+    for fmt in ("CSR", "COO"):
+        out = _run("spmm", adj, make_args(torch.int8, fmt, 32), x)
+        assert torch.equal(out, oracle_spmm(oracle, adj, x, torch.int8))
+
+
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+def test_long_rows_are_segmented(gpu_backend, oracle, fmt):
+    # one row far above seg_len (256 minimum) so the segment + fix-up path runs
+    n = 3000
+    adj = random_adj(40, n, 0.01, seed=1, long_row=3)
+    for dtype in (torch.float32, torch.int16, torch.float64, torch.int64):
+        x = features(n, 32, dtype, seed=6)
+        out = _run("spmm", adj, make_args(dtype, fmt, 32), x)
+        assert torch.equal(out, oracle_spmm(oracle, adj, x, dtype)), dtype
+
+
+def test_float_tolerance_real_valued(gpu_backend, oracle):
+    """FLT32 with real-valued inputs: |gpu - exact| <= 1e-5 * sum|a x| + 1e-6 per element."""
+    adj = random_adj(400, 400, 0.1, seed=2, value_dtype=torch.float32, long_row=8)
+    x = features(400, 64, torch.float32, seed=3, integer_valued=False)
+    rowptr, col, val = adj.csr()
+    exact, mag = oracle.spmm_csr_f32_exact(rowptr.numpy(), col.numpy(), val.numpy(), x.numpy())
+    for fmt in ("CSR", "COO"):
+        out = _run("spmm", adj, make_args(torch.float32, fmt, 64), x).double().numpy()
+        assert np.all(np.abs(out - exact) <= 1e-5 * mag + 1e-6), fmt
+
+
+def test_grande_and_spmv_frontends(gpu_backend, oracle):
+    adj = random_adj(203, 203, 0.05, seed=12)
+    for dtype in (torch.int32, torch.float32, torch.int8):
+        x = features(203, 32, dtype, seed=7)
+        want = oracle_spmm(oracle, adj, x, dtype)
+        for sp in (1, 2):
+            out = _run("grande", adj, make_args(dtype, "CSR", 32, sp, 1), x, dpus_per_rank=[5] * sp)
+            assert torch.equal(out, want), ("grande", dtype, sp)
+        out = _run("spmv", adj, make_args(dtype, "COO", 32, 1, 8), x)
+        assert out.shape == want.shape and torch.equal(out, want), ("spmv", dtype)
+
+
+def test_empty_matrix_and_empty_rows(gpu_backend, oracle):
+    adj = random_adj(50, 50, 0.0, seed=0)
+    x = features(50, 16, torch.float32)
+    for fmt in ("CSR", "COO"):
+        out = _run("spmm", adj, make_args(torch.float32, fmt, 16), x)
+        assert torch.equal(out, torch.zeros(50, 16))
