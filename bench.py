@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py - the aggregation hot path (sparse adjacency x dense features) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Reddit-shaped synthetic graph (232,965 nodes, 114,615,892 edges,
+value-less adjacency => ones, features = randint(-8, 4) as spmm_test.py:70), FLT32 CSR SpMM, hidden-size
+sweep 16/32/64/128.  One STEP = one pass of the hot path over the sweep (four SpMMs).
+
+metric  : SpMM GFLOP/s = sum_H 2*nnz*H / time (whole job, all GPUs), inputs resident in HBM.
+e2e     : the same step through the public API `prepare_pim_spmm(...).mul(x)` with HOST (pinned) operands:
+          H2D of B and D2H of C inside the timed region.
+roofline: HBM bound for the dominant kernel (the H=128 launch): algorithmic bytes
+          4(N+1) + 4 nnz + s nnz + s N H + s N H / its CUDA-event duration, against
+          MEASURED_PEAKS.json's hbm_gbs.
+N > 1   : the adjacency is row-sharded by nnz across ranks (one process per GPU), B replicated, every
+          rank computes its C row block and the blocks are all-gathered over NCCL; the collective is inside
+          the timed region ("scaling": "strong").
+--impl reference : the reference's CPU path (`--version=cpu`: row-parallel CSR SpMM on the host cores,
+          restated in oracle/spmm_oracle.c because torch_sparse is not installable) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN_SWEEP = [16, 32, 64, 128]
+SHAPE = "reddit"
+METRIC = "spmm_gflops"
+UNIT = "GFLOP/s"
+
+
+def alg_bytes_csr(n_rows, n_cols, nnz, hidden, s=4):
+    """ALGORITHMIC bytes of one CSR SpMM: rowptr + colind + values + B once + C once."""
+    return 4 * (n_rows + 1) + 4 * nnz + s * nnz + s * n_cols * hidden + s * n_rows * hidden
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_args(hidden, dtype):
+    return types.SimpleNamespace(data_type=dtype, sp_format="CSR", hidden_size=hidden, sp_parts=1, ds_parts=1)
+
+
+# ====================================================================================== CPU arms
+def cpu_spmm_sample(O, clib, rowptr, col, x_by_h, threads, repeats=1):
+    """Times the row-parallel CSR SpMM (the `--version=cpu` algorithm class) over the sweep on the given
+    row block.  Returns (seconds for one sweep pass [best of repeats], flops of one pass)."""
+    import numpy as np
+    nnz = int(rowptr[-1])
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for h, x in x_by_h.items():
+            out = np.empty((rowptr.shape[0] - 1, h), dtype=np.float32)
+            O.spmm_csr_rowpar(rowptr, col, None, x, nthreads=threads, out=out, clib=clib)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, sum(2.0 * nnz * h for h in x_by_h)
+
+
+def cpu_sample_graph(n, nnz, max_deg, sample_rows, seed=0):
+    """The first `sample_rows` rows of the Reddit-shaped graph, generated on the host."""
+    from pygim_b200 import graphgen
+    rowptr, col = graphgen.synthetic_csr(n, nnz, max_deg, seed=seed, rows=(0, sample_rows))
+    return rowptr.numpy().astype("int32"), col.numpy().astype("int32")
+
+
+def run_reference(a):
+    """--impl reference: PyGim's CPU path timed on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    from pygim_b200 import graphgen
+    O.build()
+    native = O.build_native()
+    clib = O.lib(native) if native else O.lib()
+    threads = O.max_threads()
+    n, nnz, max_deg = graphgen.SHAPES[SHAPE]
+    sample_rows = a.cpu_sample_rows or max(1024, n // 16)      # ~7 M nonzeros x the sweep per step
+    rowptr, col = cpu_sample_graph(n, nnz, max_deg, sample_rows)
+    x_by_h = {h: graphgen.reference_features(n, h, torch.float32, seed=h).numpy() for h in HIDDEN_SWEEP}
+    for _ in range(a.warmup):
+        cpu_spmm_sample(O, clib, rowptr, col, x_by_h, threads)
+    t0 = time.perf_counter()
+    flops = 0.0
+    for _ in range(a.steps):
+        _, f = cpu_spmm_sample(O, clib, rowptr, col, x_by_h, threads)
+        flops += f
+    dt = time.perf_counter() - t0
+    value = flops / dt / 1e9
+    sample = "rows [0,%d) of the Reddit-shaped graph (%d nnz), hidden sweep %s, per step" % (
+        sample_rows, int(rowptr[-1]), HIDDEN_SWEEP)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / max(a.steps, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "reddit-shape FLT32 CSR SpMM, hidden sweep 16/32/64/128", "nodes": n, "edges": nnz,
+                   "hidden_sweep": HIDDEN_SWEEP, "format": "CSR"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "native_build": bool(native)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ====================================================================================== GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the aggregation path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pygim_b200 import graphgen
+    from pygim_b200.backend_pim import pim_ops
+    from pygim_b200.backend_pim.spmm import SparseTensorCOO
+    from pygim_b200.sparse_tensor import SparseTensor
+
+    dtype = torch.float32
+    n, nnz, max_deg = graphgen.SHAPES[a.shape]
+    sweep = a.hidden if a.hidden else HIDDEN_SWEEP
+    pim_ops.dpu_init_ranks(1)
+    info = pim_ops.device_info()
+
+    # ---- this rank's row shard (nnz-balanced, the GPU-level partition_by_nnz_csr)
+    deg = graphgen.degree_sequence(n, nnz, max_deg, n, seed=0)
+    full_rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(deg, 0, out=full_rowptr[1:])
+    splits = pim_ops.partition_rows_by_nnz(full_rowptr, world) if world > 1 else [0, n]
+    r0, r1 = splits[rank], splits[rank + 1]
+    rowptr, col = graphgen.synthetic_csr(n, nnz, max_deg, seed=0, device=str(dev), rows=(r0, r1), deg=deg)
+    shard_nnz = int(col.numel())
+    adj = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(r1 - r0, n), is_sorted=True)
+    del rowptr, col
+    base = SparseTensorCOO(adj, dtype=dtype, format="CSR")
+    base.build_csr()
+    plans = {}
+    for h in sweep:
+        A = copy.copy(base)          # shares the int32 CSR arrays; one plan per hidden size
+        A.sp_info_ptr = None
+        A.to_pim_group(h, 1)
+        plans[h] = A
+    x_dev = {h: graphgen.reference_features(n, h, dtype, seed=h, device=str(dev)) for h in sweep}
+    # full outputs (every rank ends with all rows, ready for the next layer)
+    c_full = {h: torch.empty((n, h), dtype=dtype, device=dev) for h in sweep}
+    row_counts = [splits[i + 1] - splits[i] for i in range(world)]
+
+    def step_device(record=None):
+        for i, h in enumerate(sweep):
+            if record is not None:
+                record[i][0].record()
+            out = c_full[h][r0:r1]
+            plans[h].mul(x_dev[h], out=out)
+            if record is not None:
+                record[i][1].record()
+            if world > 1:
+                chunks = list(torch.split(c_full[h], row_counts, dim=0))
+                dist.all_gather(chunks, out)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in sweep]
+          for _ in range(a.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t_begin.record()
+    for k in range(a.steps):
+        step_device(ev[k])
+    t_end.record()
+    sync()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    launches_per_step = sum(pim_ops.last_launches(plans[h].sp_info_ptr) for h in sweep)
+    per_h_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(a.steps)) / a.steps
+                for i in range(len(sweep))]
+    if world > 1:
+        t = torch.tensor([elapsed_ms] + per_h_ms, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, per_h_ms = float(t[0]), [float(v) for v in t[1:]]
+    clocks = sampler.stop() if rank == 0 else None
+
+    flops_step = sum(2.0 * nnz * h for h in sweep)
+    value = flops_step * a.steps / (elapsed_ms * 1e-3) / 1e9
+
+    # ---- e2e: same step through the public API with pinned HOST operands (H2D + D2H inside the timing)
+    x_host = {h: x_dev[h].cpu().pin_memory() for h in sweep}
+    c_host = {h: torch.empty((r1 - r0, h), dtype=dtype).pin_memory() for h in sweep}
+
+    def step_host():
+        for h in sweep:
+            plans[h].mul(x_host[h], out=c_host[h])
+
+    e2e_steps = max(3, min(a.steps, 10))
+    for _ in range(2):
+        step_host()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    sync()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = flops_step * e2e_steps / e2e_s / 1e9
+    h2d = sum(n * h * 4 for h in sweep)
+    d2h = sum((r1 - r0) * h * 4 for h in sweep)
+    timers = {h: pim_ops.last_timers(plans[h].sp_info_ptr) for h in sweep}
+
+    # ---- parity spot check of what was just timed (rank 0, first rows, against the oracle)
+    parity = None
+    if rank == 0 and not a.no_check:
+        import numpy as np
+        from oracle import oracle as O
+        O.build()
+        rows_chk = min(256, r1 - r0)
+        rp, cl, _ = adj.csr()
+        rp_h = rp[: rows_chk + 1].cpu().numpy().astype("int32")
+        cl_h = cl[: int(rp_h[-1])].cpu().numpy().astype("int32")
+        parity = True
+        for h in sweep:
+            want = O.spmm_csr_rowpar(rp_h, cl_h, None, x_host[h].numpy())
+            parity = parity and bool(np.array_equal(want, c_full[h][r0:r0 + rows_chk].cpu().numpy())) \
+                and bool(np.array_equal(want, c_host[h][:rows_chk].numpy()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest share of the step)
+    peak, peak_kind = measured_peaks()
+    dom = max(range(len(sweep)), key=lambda i: per_h_ms[i])
+    per_hidden = []
+    for i, h in enumerate(sweep):
+        # per-GPU algorithmic bytes of this rank's launch (shard of A and C, all of B)
+        b = alg_bytes_csr(r1 - r0, n, shard_nnz, h)
+        per_hidden.append({"hidden": h, "kernel_ms": per_h_ms[i], "gflops": 2.0 * shard_nnz * h / per_h_ms[i] / 1e6,
+                           "alg_gbs": b / per_h_ms[i] / 1e6, "frac_hbm": b / per_h_ms[i] / 1e6 / peak,
+                           "gather_gbs": 4.0 * shard_nnz * h / per_h_ms[i] / 1e6})
+    roof = {"bound": "hbm", "kernel": "csr_spmm_kernel<float,4,%d> (hidden %d)" % (min(32, sweep[dom] // 4), sweep[dom]),
+            "achieved": per_hidden[dom]["alg_gbs"], "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+            "frac": per_hidden[dom]["frac_hbm"], "traffic": None,
+            "alg_bytes_per_launch": alg_bytes_csr(r1 - r0, n, shard_nnz, sweep[dom]),
+            "sweep_achieved": sum(alg_bytes_csr(r1 - r0, n, shard_nnz, h) for h in sweep) / sum(per_h_ms) / 1e6,
+            "note": "Reddit-shape is L2-gather bound (s*nnz*H bytes leave L2 per launch), see DESIGN.md"}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            with open(traffic_path) as f:
+                roof["traffic"] = json.load(f).get(str(sweep[dom]))
+        except Exception:
+            pass
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        from oracle import oracle as O
+        O.build()
+        native = O.build_native()
+        clib = O.lib(native) if native else O.lib()
+        threads = O.max_threads()
+        sample_rows = a.cpu_sample_rows or max(1024, n // 16)
+        rp, cl, _ = adj.csr()
+        rp_h = rp[: sample_rows + 1].cpu().numpy().astype("int32")
+        cl_h = cl[: int(rp_h[-1])].cpu().numpy().astype("int32")
+        xs = {h: x_host[h].numpy() for h in sweep}
+        secs, fl = cpu_spmm_sample(O, clib, rp_h, cl_h, xs, threads, repeats=2)
+        cpu = {"value": fl / secs / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "rows [0,%d) of the same graph (%d nnz), hidden sweep %s, best of 2 (%.1f s each)"
+                         % (sample_rows, int(rp_h[-1]), sweep, secs), "native_build": bool(native)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s-shape FLT32 CSR SpMM, hidden sweep %s" % (a.shape, "/".join(map(str, sweep))),
+                   "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": "CSR", "sp_parts": 1, "ds_parts": 1,
+                   "sharding": "rows by nnz over %d GPU(s), B replicated, NCCL all-gather of C inside the timing" % world
+                   if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (A = %.0f MB streams through a %.0f MB L2 every launch)"
+                         % ((8.0 * nnz) / 1e6, info["l2_bytes"] / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+                "phases_ms": {str(h): timers[h] for h in sweep}},
+        "gpu_launches": launches_per_step * a.steps,
+        "roofline": roof, "per_hidden": per_hidden, "cpu_baseline": cpu, "clocks": clocks,
+        "parity_spot_check": parity,
+        "lib": os.path.relpath(__import__("pygim_b200._lib", fromlist=["x"]).loaded_path() or "", ROOT),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default=SHAPE, choices=["reddit", "products", "arxiv"])
+    ap.add_argument("--hidden", type=int, nargs="*", default=None, help="override the hidden sweep")
+    ap.add_argument("--cpu-sample-rows", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

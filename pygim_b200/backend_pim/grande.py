@@ -62,12 +62,12 @@ class SparseTensorCOO(SparseTensorBase):
             [p.values() for p in self.csr], [p.size(0) for p in self.csr], [p.size(1) for p in self.csr],
             self.dense_ncols, hidden_size)
 
-    def mul(self, B: torch.Tensor):
+    def mul(self, B: torch.Tensor, out=None):
         assert self.hidden_size == B.size(1)
         assert len(self.dpus_per_rank) == len(self.csr)
         if self.format != "CSR":
             return None
-        return pim_ops.spmm_run_dense(self.sp_info_ptr, B)
+        return pim_ops.spmm_run_dense(self.sp_info_ptr, B, out=out)
 
 
 def prepare_pim_spmm_grande(adj_t, args, dpus_per_rank):

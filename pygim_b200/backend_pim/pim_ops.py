@@ -245,9 +245,18 @@ def spmv_coo_run_group(handle: int, B_parts: Sequence[torch.Tensor]) -> torch.Te
     return _run_group(handle, B_parts)
 
 
-def spmm_run_dense(handle: int, B: torch.Tensor) -> torch.Tensor:
+def _check_out(out: torch.Tensor, m: _GroupMeta, like: torch.Tensor) -> torch.Tensor:
+    if out.dtype != m.dtype or tuple(out.shape) != (m.total_rows, m.h_size) or out.is_cuda != like.is_cuda or \
+            (out.numel() and out.stride(1) != 1):
+        raise _lib.PygimError("out= must be a row-major (%d, %d) %s tensor on the operand's device"
+                              % (m.total_rows, m.h_size, m.dtype))
+    return out
+
+
+def spmm_run_dense(handle: int, B: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fast path used by SparseTensorCOO.mul: the whole [sum ncols x h_size] operand in one piece, so
-    the dense_split copies of spmm.py:9-13 are not needed - dense parts become column tiles."""
+    the dense_split copies of spmm.py:9-13 are not needed - dense parts become column tiles.
+    `out` (optional) is a preallocated result, e.g. a pinned host tensor for full-rate D2H."""
     m = _meta(handle)
     if B.dtype != m.dtype:
         raise _lib.PygimError("dense operand dtype %s does not match the plan's %s" % (B.dtype, m.dtype))
@@ -258,10 +267,12 @@ def spmm_run_dense(handle: int, B: torch.Tensor) -> torch.Tensor:
     lib = _lib.lib()
     ldb = B.stride(0) if B.size(0) > 1 else max(B.size(1), 1)
     if B.is_cuda:
-        out = torch.empty((m.total_rows, m.h_size), dtype=m.dtype, device=B.device)
+        out = torch.empty((m.total_rows, m.h_size), dtype=m.dtype, device=B.device) if out is None \
+            else _check_out(out, m, B)
+        ldc = out.stride(0) if out.size(0) > 1 else max(m.h_size, 1)
         with torch.cuda.device(B.device):
             stream = torch.cuda.current_stream(B.device).cuda_stream
-            _lib.check(lib.pygim_spmm_device(int(handle), B.data_ptr(), ldb, out.data_ptr(), m.h_size,
+            _lib.check(lib.pygim_spmm_device(int(handle), B.data_ptr(), ldb, out.data_ptr(), ldc,
                                              C.c_void_p(stream)))
         return out
     # host operand: present the column tiles as views of B (no copies) to the host entry point
@@ -269,9 +280,10 @@ def spmm_run_dense(handle: int, B: torch.Tensor) -> torch.Tensor:
     for w in m.dense_cols:
         parts.append(B[:, col:col + w])
         col += w
-    out = torch.empty((m.total_rows, m.h_size), dtype=m.dtype)
+    out = torch.empty((m.total_rows, m.h_size), dtype=m.dtype) if out is None else _check_out(out, m, B)
+    ldc = out.stride(0) if out.size(0) > 1 else max(m.h_size, 1)
     _lib.check(lib.pygim_spmm_run_group_host(int(handle), len(parts), _ptr_array(parts),
-                                             _i64_array([ldb] * len(parts)), out.data_ptr(), m.h_size))
+                                             _i64_array([ldb] * len(parts)), out.data_ptr(), ldc))
     return out
 
 

@@ -56,14 +56,14 @@ class SparseTensorCOO(SparseTensorBase):
         else:
             assert False
 
-    def mul(self, B: torch.Tensor):
+    def mul(self, B: torch.Tensor, out=None):
         assert self.hidden_size == B.size(1)
         if self.format not in ("CSR", "COO"):
             return None
         # torch.chunk and split_widths disagree when ds_parts does not divide well (e.g. 10 columns in
         # 4 parts: chunk gives 3,3,3,1 and 3 parts would be missing for 9 in 4); the reference then
         # trips its asserts.  The column tiles of the plan are authoritative here, so B is passed whole.
-        return pim_ops.spmm_run_dense(self.sp_info_ptr, B)
+        return pim_ops.spmm_run_dense(self.sp_info_ptr, B, out=out)
 
 
 def prepare_pim_spmm(adj_t, args):

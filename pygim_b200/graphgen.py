@@ -83,13 +83,23 @@ def degree_sequence(n: int, nnz: int, max_deg: int, ncols: Optional[int] = None,
 
 
 def synthetic_csr(n: int, nnz: int, max_deg: int, ncols: Optional[int] = None, seed: int = 0,
-                  device: str = "cpu") -> Tuple[torch.Tensor, torch.Tensor]:
-    """(rowptr int64[n+1], col int64[nnz]) of a random graph with the given shape."""
+                  device: str = "cpu", rows: Optional[Tuple[int, int]] = None,
+                  deg: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(rowptr int64[n+1], col int64[nnz]) of a random graph with the given shape.  `rows=(r0, r1)`
+    generates only that row block (a shard: rowptr has r1-r0+1 entries starting at 0) of the SAME degree
+    sequence; the column jitter of a shard is seeded by (seed, r0)."""
     m = n if ncols is None else ncols
-    deg = degree_sequence(n, nnz, max_deg, m, seed).to(device)
+    if deg is None:
+        deg = degree_sequence(n, nnz, max_deg, m, seed)
+    jitter_seed = seed + 1
+    if rows is not None:
+        deg = deg[rows[0]:rows[1]]
+        n, nnz = int(deg.numel()), int(deg.sum())
+        jitter_seed = seed + 1 + 7919 * rows[0]
+    deg = deg.to(device)
     rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
     torch.cumsum(deg, 0, out=rowptr[1:])
-    gen = torch.Generator(device=device).manual_seed(seed + 1)
+    gen = torch.Generator(device=device).manual_seed(jitter_seed)
     col = torch.empty(nnz, dtype=torch.int64, device=device)
     # chunked over nnz so the temporaries stay small next to a 114.6 M-edge graph
     rows_per_chunk = max(1, int(n * (32_000_000 / max(nnz, 1))))

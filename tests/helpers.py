@@ -13,8 +13,11 @@ NP_DTYPES = {torch.int8: np.int8, torch.int16: np.int16, torch.int32: np.int32, 
 ALL_DTYPES = list(NP_DTYPES)
 
 
-def random_adj(n, m, density, seed=0, value_dtype=None, empty_rows=(), long_row=None, value_range=(-5, 6)):
-    """SparseTensor with sorted unique indices.  value_dtype None => value-less (implicit ones)."""
+def random_adj(n, m, density, seed=0, value_dtype=None, empty_rows=(), long_row=None, value_range=(-5, 6),
+               real_valued=False):
+    """SparseTensor with sorted unique indices.  value_dtype None => value-less (implicit ones).  Float
+    values are integer-valued unless real_valued (integer-valued floats make f32/f64 sums exact, so the
+    comparison with the oracle can be bit-exact regardless of summation order)."""
     rng = np.random.default_rng(seed)
     mask = rng.random((n, m)) < density
     for r in empty_rows:
@@ -24,7 +27,7 @@ def random_adj(n, m, density, seed=0, value_dtype=None, empty_rows=(), long_row=
     row, col = np.nonzero(mask)
     value = None
     if value_dtype is not None:
-        if value_dtype.is_floating_point:
+        if value_dtype.is_floating_point and real_valued:
             value = torch.from_numpy(rng.standard_normal(row.shape[0])).to(value_dtype)
         else:
             value = torch.from_numpy(rng.integers(value_range[0], value_range[1], row.shape[0])).to(value_dtype)

@@ -78,7 +78,7 @@ def test_long_rows_are_segmented(gpu_backend, oracle, fmt):
 
 def test_float_tolerance_real_valued(gpu_backend, oracle):
     """FLT32 with real-valued inputs: |gpu - exact| <= 1e-5 * sum|a x| + 1e-6 per element."""
-    adj = random_adj(400, 400, 0.1, seed=2, value_dtype=torch.float32, long_row=8)
+    adj = random_adj(400, 400, 0.1, seed=2, value_dtype=torch.float32, long_row=8, real_valued=True)
     x = features(400, 64, torch.float32, seed=3, integer_valued=False)
     rowptr, col, val = adj.csr()
     exact, mag = oracle.spmm_csr_f32_exact(rowptr.numpy(), col.numpy(), val.numpy(), x.numpy())
