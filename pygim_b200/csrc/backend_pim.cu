@@ -115,6 +115,9 @@ struct Group {
     std::vector<long long> dense_cols;
     // options (< 0 = automatic)
     long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1;
+    // dynamic work distribution of the persistent CSR kernel: a device ticket counter that only grows
+    unsigned long long *d_ticket = nullptr;
+    unsigned long long ticket_base = 0;
     // scratch
     void *d_partial = nullptr;
     size_t partial_bytes = 0;
@@ -205,6 +208,7 @@ static void destroy_group(Group *g) {
         }
     }
     if (g->d_partial) cudaFree(g->d_partial);
+    if (g->d_ticket) cudaFree(g->d_ticket);
     if (g->d_B) cudaFree(g->d_B);
     if (g->d_C) cudaFree(g->d_C);
     for (auto &e : g->ev)
@@ -268,6 +272,9 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.ldc = ldc;
         l.ldp = ldp;
         l.accumulate = accumulate ? 1 : 0;
+        l.sm_count = g_ctx.sm_count;
+        l.ticket = g->d_ticket;
+        l.ticket_base = &g->ticket_base;
         l.stream = stream;
         err = dispatch_csr(g->dtype, l, &g->last_launches);
     } else {
@@ -450,6 +457,11 @@ PYGIM_API int pygim_spmm_to_device_group(int format, int dtype, int n_sp, const 
             int rc = build_csr_plan(p, auto_seg_len(p));
             if (rc) return bail(rc);
         }
+    }
+    {
+        cudaError_t ce = cudaMalloc(&g->d_ticket, sizeof(unsigned long long));
+        if (ce == cudaSuccess) ce = cudaMemset(g->d_ticket, 0, sizeof(unsigned long long));
+        if (ce != cudaSuccess) return bail(fail(PYGIM_ERR_CUDA, "ticket counter setup failed: %s", cudaGetErrorString(ce)));
     }
     for (auto &e : g->ev) {
         cudaError_t ce = cudaEventCreate(&e);

@@ -30,6 +30,35 @@ static int pow2_ceil(long long v) {
     return g;
 }
 
+// UNROLL independent 16-byte gathers per lane; MIN_BLOCKS resident 256-thread blocks per SM
+template <int E, int G> struct CsrTune {
+    static constexpr int UNROLL = (G < 8) ? G : 8;
+    static constexpr int MIN_BLOCKS = (sizeof(T) * E * UNROLL > 64) ? 3 : 4;
+};
+
+template <int E, int G> static cudaError_t launch_csr_g(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
+    auto kernel = csr_spmm_kernel<T, E, G, CsrTune<E, G>::UNROLL, CsrTune<E, G>::MIN_BLOCKS>;
+    static int blocks_per_sm = 0;   // per instantiation
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kCsrThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    a.col_chunks = (a.nvec + G - 1) / G;
+    const unsigned long long total = (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + a.nrows);
+    const unsigned long long warps_needed = total;
+    unsigned long long blocks = (unsigned long long)blocks_per_sm * (l.sm_count > 0 ? l.sm_count : 148);
+    const unsigned long long blocks_needed = (warps_needed + (kCsrThreads / 32) - 1) / (kCsrThreads / 32);
+    if (blocks > blocks_needed) blocks = blocks_needed;
+    a.ticket = l.ticket;
+    a.ticket_base = *l.ticket_base;
+    kernel<<<(unsigned)blocks, kCsrThreads, 0, l.stream>>>(a);
+    // every warp draws tickets until it sees one past the end: total + (#warps) tickets per launch
+    *l.ticket_base += total + blocks * (kCsrThreads / 32);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *launches) {
     CsrArgs<T> a;
     a.rowptr = l.rowptr;
@@ -49,19 +78,15 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.accumulate = l.accumulate;
     const long long items = (long long)l.n_seg + l.nrows;
     if (items == 0 || a.nvec == 0) return cudaSuccess;
-    const int G = pow2_ceil(a.nvec);
-    dim3 grid((unsigned)((items + kCsrWarpsPerBlock - 1) / kCsrWarpsPerBlock), (unsigned)((a.nvec + G - 1) / G));
-    dim3 block(kCsrWarpsPerBlock * 32);
-    switch (G) {
-        case 1: csr_spmm_kernel<T, E, 1><<<grid, block, 0, l.stream>>>(a); break;
-        case 2: csr_spmm_kernel<T, E, 2><<<grid, block, 0, l.stream>>>(a); break;
-        case 4: csr_spmm_kernel<T, E, 4><<<grid, block, 0, l.stream>>>(a); break;
-        case 8: csr_spmm_kernel<T, E, 8><<<grid, block, 0, l.stream>>>(a); break;
-        case 16: csr_spmm_kernel<T, E, 16><<<grid, block, 0, l.stream>>>(a); break;
-        default: csr_spmm_kernel<T, E, 32><<<grid, block, 0, l.stream>>>(a); break;
+    cudaError_t err;
+    switch (pow2_ceil(a.nvec)) {
+        case 1: err = launch_csr_g<E, 1>(a, l, launches); break;
+        case 2: err = launch_csr_g<E, 2>(a, l, launches); break;
+        case 4: err = launch_csr_g<E, 4>(a, l, launches); break;
+        case 8: err = launch_csr_g<E, 8>(a, l, launches); break;
+        case 16: err = launch_csr_g<E, 16>(a, l, launches); break;
+        default: err = launch_csr_g<E, 32>(a, l, launches); break;
     }
-    ++*launches;
-    cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     if (l.n_long > 0) {
         FixupArgs<T> f;

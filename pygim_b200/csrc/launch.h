@@ -22,6 +22,9 @@ struct CsrLaunch {
     long long ncols;          // dense columns of this tile
     long long ldb, ldc, ldp;  // row strides in elements
     int accumulate;
+    int sm_count;
+    unsigned long long *ticket;        // device work counter of the plan (monotonic)
+    unsigned long long *ticket_base;   // host mirror: value of *ticket when the next launch starts
     cudaStream_t stream;
 };
 

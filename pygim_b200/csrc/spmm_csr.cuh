@@ -4,13 +4,17 @@
 // multigroup copies).  Where a DPU tasklet walks a contiguous row block and issues one MRAM read
 // of dense_size*byte_dt bytes per nonzero (:108-126), here:
 //
-//  * one warp owns one work item: a whole row, or - for rows longer than seg_len - one
-//    seg_len-bounded segment of a row (the nnz-balanced second level of the reference's
-//    partition_tsklt_by_nnz_csr, support/partition.c:186-229, taken to exact nnz granularity);
-//  * the warp reads 32 column indices and 32 values with one coalesced, evict-first load each and
-//    hands them round with shuffles;
+//  * the grid is PERSISTENT (resident warps only); every warp pulls work items from a global
+//    ticket counter, so no warp idles while another still owns a long row (the reference's
+//    second-level balancing, partition_tsklt_by_nnz_csr, support/partition.c:186-229, made dynamic);
+//  * a work item is a whole row, or - for rows longer than seg_len - one seg_len-bounded segment
+//    of a row; segment items come first in ticket order, longest first;
+//  * the warp reads 32 column indices and 32 values per coalesced evict-first load, TWO batches
+//    ahead of the one being consumed, and hands them round with shuffles: the HBM latency of the
+//    index stream is off the critical path of the gathers;
+//  * the next item's ticket and row bounds are fetched before the current item is processed;
 //  * a dense row of H elements is covered by G lanes, each moving one 16-byte word (float4,
-//    16 x int8, ...), so P = 32/G nonzeros are gathered by every load instruction and up to UNROLL
+//    16 x int8, ...), so P = 32/G nonzeros are gathered by every load instruction and UNROLL
 //    independent gathers per lane are in flight before the first FMA consumes one;
 //  * the P partial sums are combined by an xor-shuffle tree in a fixed order (deterministic), and
 //    the row is written once with a streaming store - no host merge (memcpy_2D / memadd_2D,
@@ -37,32 +41,85 @@ template <typename T> struct CsrArgs {
     T *C;              // output, row stride ldc elements
     T *partial;        // [n_seg x ldp] scratch for segment items
     const Seg *segs;
+    unsigned long long *ticket;      // monotonically increasing work counter (never reset)
+    unsigned long long ticket_base;  // its value when this launch starts
     int n_seg;
     int nrows;
     int seg_len;       // rows with more nonzeros than this are handled through segs
     int nvec;          // words (of E elements) per dense row
+    int col_chunks;    // ceil(nvec / G): every item is processed once per chunk of G words
     long long ldb, ldc, ldp;
     int accumulate;    // 0: C = A*B, 1: C += A*B
 };
 
-constexpr int kCsrWarpsPerBlock = 8;
+constexpr int kCsrThreads = 256;
+
+struct CsrItem {
+    int start, end;    // nonzero range
+    int row;           // output row (C) or slot (partial)
+    int chunk;         // column chunk
+    bool to_partial;
+    bool skip;
+};
+
+template <typename T, int G>
+__device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, unsigned long long it) {
+    CsrItem r;
+    const unsigned long long items = (unsigned long long)a.n_seg + (unsigned long long)a.nrows;
+    r.chunk = (int)(it / items);
+    const long long k = (long long)(it % items);
+    if (k < a.n_seg) {
+        const Seg sg = a.segs[k];
+        r.start = sg.start;
+        r.end = sg.end;
+        r.row = sg.slot;
+        r.to_partial = true;
+        r.skip = false;
+    } else {
+        r.row = (int)(k - a.n_seg);
+        r.start = a.rowptr[r.row];
+        r.end = a.rowptr[r.row + 1];
+        r.to_partial = false;
+        r.skip = (r.end - r.start) > a.seg_len;   // covered by its segments + fix-up
+    }
+    return r;
+}
 
 template <typename T, int E, int G, int UNROLL>
-__device__ __forceinline__ void csr_gather_range(const CsrArgs<T> &a, int start, int end, const T *Bcol, bool active,
-                                                 typename Arith<T>::Acc (&acc)[E]) {
+__device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrItem &item) {
+    using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
     constexpr int P = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int sub = lane / G;
+    const int vec = item.chunk * G + (lane % G);
+    const bool active = vec < a.nvec;
+    const T *Bcol = a.B + (long long)vec * E;
+    const int end = item.end;
 
-    for (int base = start; base < end; base += 32) {
-        const int idx = base + lane;
-        int c = 0;
-        Shfl v = 0;
-        if (idx < end) {
-            c = ld_stream(a.colind + idx);
-            v = ld_stream(a.val + idx);
+    Acc acc[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+
+    // index/value stream, prefetched two batches (64 nonzeros) ahead of the gathers
+    int c0 = 0, c1 = 0;
+    Shfl v0 = 0, v1 = 0;
+    {
+        const int i0 = item.start + lane, i1 = item.start + 32 + lane;
+        if (i0 < end) { c0 = ld_stream(a.colind + i0); v0 = ld_stream(a.val + i0); }
+        if (i1 < end) { c1 = ld_stream(a.colind + i1); v1 = ld_stream(a.val + i1); }
+    }
+    for (int base = item.start; base < end; base += 32) {
+        const int c = c0;
+        const Shfl v = v0;
+        c0 = c1;
+        v0 = v1;
+        c1 = 0;
+        v1 = 0;
+        {
+            const int i2 = base + 64 + lane;
+            if (i2 < end) { c1 = ld_stream(a.colind + i2); v1 = ld_stream(a.val + i2); }
         }
         const int rem = end - base;
         if (rem >= 32) {
@@ -70,17 +127,15 @@ __device__ __forceinline__ void csr_gather_range(const CsrArgs<T> &a, int start,
 #pragma unroll
             for (int s0 = 0; s0 < G; s0 += UNROLL) {
                 Pack<T, E> b[UNROLL];
-                Shfl vv[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
-                    const int src = (s0 + u) * P + sub;
-                    const int cc = __shfl_sync(FULL, c, src);
-                    vv[u] = __shfl_sync(FULL, v, src);
+                    const int cc = __shfl_sync(FULL, c, (s0 + u) * P + sub);
                     if (active) b[u] = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
                 }
-                if (active) {
 #pragma unroll
-                    for (int u = 0; u < UNROLL; ++u) fma_pack<T, E>(acc, b[u], vv[u]);
+                for (int u = 0; u < UNROLL; ++u) {
+                    const Shfl vv = __shfl_sync(FULL, v, (s0 + u) * P + sub);
+                    if (active) fma_pack<T, E>(acc, b[u], vv);
                 }
             }
         } else {
@@ -97,46 +152,6 @@ __device__ __forceinline__ void csr_gather_range(const CsrArgs<T> &a, int start,
             }
         }
     }
-}
-
-// grid.x = ceil((n_seg + nrows) / kCsrWarpsPerBlock); grid.y = column chunks of G words (only > 1 when G == 32)
-template <typename T, int E, int G>
-__global__ void __launch_bounds__(kCsrWarpsPerBlock * 32) csr_spmm_kernel(const CsrArgs<T> a) {
-    using Acc = typename Arith<T>::Acc;
-    constexpr int P = 32 / G;
-    constexpr int UNROLL = (G < 8) ? G : 8;
-    constexpr unsigned FULL = 0xffffffffu;
-
-    const long long item = (long long)blockIdx.x * kCsrWarpsPerBlock + (threadIdx.x >> 5);
-    if (item >= (long long)a.n_seg + a.nrows) return;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / G;
-    const int vec = blockIdx.y * G + (lane % G);
-    const bool active = vec < a.nvec;
-
-    int start, end;
-    T *dst;
-    bool accumulate = a.accumulate != 0;
-    if (item < a.n_seg) {
-        // long-row segments come first so the biggest items are scheduled earliest
-        const Seg sg = a.segs[item];
-        start = sg.start;
-        end = sg.end;
-        dst = a.partial + (long long)sg.slot * a.ldp;
-        accumulate = false;
-    } else {
-        const int row = (int)(item - a.n_seg);
-        start = a.rowptr[row];
-        end = a.rowptr[row + 1];
-        if (end - start > a.seg_len) return;   // handled by its segments + fix-up
-        dst = a.C + (long long)row * a.ldc;
-    }
-
-    Acc acc[E];
-#pragma unroll
-    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
-
-    csr_gather_range<T, E, G, UNROLL>(a, start, end, a.B + (long long)vec * E, active, acc);
 
     // combine the P interleaved partial sums; fixed tree => bitwise reproducible
 #pragma unroll
@@ -145,9 +160,42 @@ __global__ void __launch_bounds__(kCsrWarpsPerBlock * 32) csr_spmm_kernel(const 
         for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
     }
     if (sub == 0 && active) {
-        T *p = dst + (long long)vec * E;
-        if (accumulate) add_old<T, E>(acc, ld_plain<T, E>(p));
-        st_stream<T, E>(p, narrow<T, E>(acc));
+        if (item.to_partial) {
+            st_plain<T, E>(a.partial + (long long)item.row * a.ldp + (long long)vec * E, narrow<T, E>(acc));
+        } else {
+            T *p = a.C + (long long)item.row * a.ldc + (long long)vec * E;
+            if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(p));
+            st_stream<T, E>(p, narrow<T, E>(acc));
+        }
+    }
+}
+
+// Persistent grid: gridDim.x = resident blocks of the device.  Tickets run over
+// col_chunks * (n_seg + nrows) items, column chunk outermost.
+template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const CsrArgs<T> a) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long total =
+        (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + (unsigned long long)a.nrows);
+
+    auto take_ticket = [&]() -> unsigned long long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1ULL) - a.ticket_base;
+        return __shfl_sync(FULL, t, 0);
+    };
+
+    unsigned long long it = take_ticket();
+    CsrItem cur;
+    if (it < total) cur = csr_load_item<T, G>(a, it);
+    while (it < total) {
+        // look ahead: the next ticket and its row bounds are in flight while this item is processed
+        const unsigned long long nit = take_ticket();
+        CsrItem nxt;
+        if (nit < total) nxt = csr_load_item<T, G>(a, nit);
+        if (!cur.skip) csr_process_item<T, E, G, UNROLL>(a, cur);
+        it = nit;
+        cur = nxt;
     }
 }
 
