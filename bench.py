@@ -106,6 +106,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def auto_ds_parts(n_cols, hidden, info, s=4):
+    """Column tiling so that one B tile stays L2-resident next to the streaming A: see pygim_b200.utils.autotuner."""
+    from pygim_b200.utils import autotuner
+    return autotuner.choose_ds_parts(n_cols, hidden, s, info["l2_bytes"])
+
+
 def make_args(hidden, dtype):
     return types.SimpleNamespace(data_type=dtype, sp_format="CSR", hidden_size=hidden, sp_parts=1, ds_parts=1)
 
@@ -218,7 +224,7 @@ def run_ours(a):
     for h in sweep:
         A = copy.copy(base)          # shares the int32 CSR arrays; one plan per hidden size
         A.sp_info_ptr = None
-        A.to_pim_group(h, 1)
+        A.to_pim_group(h, a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, info))
         plans[h] = A
     x_dev = {h: graphgen.reference_features(n, h, dtype, seed=h, device=str(dev)) for h in sweep}
     # full outputs (every rank ends with all rows, ready for the next layer)
@@ -279,8 +285,8 @@ def run_ours(a):
         for h in sweep:
             plans[h].mul(x_host[h], out=c_host[h])
 
-    e2e_steps = max(3, min(a.steps, 10))
-    for _ in range(2):
+    e2e_steps = max(3, min(a.steps, 10)) if not a.no_e2e else 1
+    for _ in range(2 if not a.no_e2e else 0):
         step_host()
     sync()
     t0 = time.perf_counter()
@@ -365,7 +371,8 @@ def run_ours(a):
         "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s-shape FLT32 CSR SpMM, hidden sweep %s" % (a.shape, "/".join(map(str, sweep))),
-                   "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": "CSR", "sp_parts": 1, "ds_parts": 1,
+                   "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": "CSR", "sp_parts": 1,
+                   "ds_parts": {str(h): plans[h].dense_parts for h in sweep},
                    "sharding": "rows by nnz over %d GPU(s), B replicated, NCCL all-gather of C inside the timing" % world
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (A = %.0f MB streams through a %.0f MB L2 every launch)"
@@ -394,6 +401,8 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs: one untimed-quality e2e pass only")
+    ap.add_argument("--ds-parts", type=int, default=0, help="dense column parts per launch group; 0 = automatic")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -63,6 +63,7 @@ def _declare(lib: C.CDLL) -> None:
 def load(path: Optional[str] = None) -> C.CDLL:
     """dlopen the backend (the role of torch.ops.load_library(args.lib_path), spmm_test.py:111)."""
     global _lib, _lib_path
+    path = path or os.environ.get("PYGIM_LIB_PATH")   # tuning variants: python -m pygim_b200.build -D... -o ...
     path = os.path.abspath(path) if path else DEFAULT_LIB_PATH
     if _lib is not None and _lib_path == path:
         return _lib

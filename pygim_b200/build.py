@@ -54,12 +54,27 @@ def _run(cmd):
     return r.stdout
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=None, out: str = None) -> str:
+    """`defines` (e.g. ["PYGIM_CSR_UNROLL=4"]) + `out` build a tuning variant next to the default library."""
+    global LIB, OBJ
+    lib_default, obj_default = LIB, OBJ
+    if defines or out:
+        assert out, "a variant build needs an output name"
+        LIB = os.path.join(HERE, out)
+        OBJ = os.path.join(CSRC, "build_" + os.path.splitext(out)[0])
+        force = True
+    try:
+        return _build(force, verbose, list(defines or []))
+    finally:
+        LIB, OBJ = lib_default, obj_default
+
+
+def _build(force: bool, verbose: bool, defines) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-D" + d for d in defines]
     jobs = []
     for ctype, sfx in DTYPES:
         obj = os.path.join(OBJ, "kernels_%s.o" % sfx)
@@ -82,6 +97,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("-D", dest="defines", action="append", default=[])
+    ap.add_argument("-o", dest="out", default=None, help="file name of a tuning variant, e.g. libbackend_pim_u4.so")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, defines=a.defines, out=a.out))
     sys.exit(0)

@@ -30,14 +30,30 @@ static int pow2_ceil(long long v) {
     return g;
 }
 
-// UNROLL independent 16-byte gathers per lane; MIN_BLOCKS resident 256-thread blocks per SM
+// Tuning knobs (overridable at build time for experiments: -DPYGIM_CSR_UNROLL=.. etc.)
+//   UNROLL     independent gathers per lane in flight before the first FMA
+//   R          index entries per lane per batch (batch = 32*R nonzeros); R*G >= UNROLL keeps UNROLL usable
+//   D          batches of the index stream prefetched ahead
+//   MIN_BLOCKS resident 256-thread blocks per SM the register allocation must allow
+#ifndef PYGIM_CSR_UNROLL
+#define PYGIM_CSR_UNROLL 8
+#endif
+#ifndef PYGIM_CSR_MINBLOCKS
+#define PYGIM_CSR_MINBLOCKS 3
+#endif
+#ifndef PYGIM_CSR_PREFETCH
+#define PYGIM_CSR_PREFETCH 2
+#endif
 template <int E, int G> struct CsrTune {
-    static constexpr int UNROLL = (G < 8) ? G : 8;
-    static constexpr int MIN_BLOCKS = (sizeof(T) * E * UNROLL > 64) ? 3 : 4;
+    static constexpr int UNROLL = PYGIM_CSR_UNROLL;
+    static constexpr int R = (G >= UNROLL) ? 1 : ((UNROLL / G) > 4 ? 4 : (UNROLL / G));
+    static constexpr int D = (R > 1) ? 1 : PYGIM_CSR_PREFETCH;
+    static constexpr int MIN_BLOCKS = (sizeof(T) * E >= 16) ? PYGIM_CSR_MINBLOCKS : 4;
 };
 
 template <int E, int G> static cudaError_t launch_csr_g(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
-    auto kernel = csr_spmm_kernel<T, E, G, CsrTune<E, G>::UNROLL, CsrTune<E, G>::MIN_BLOCKS>;
+    auto kernel = csr_spmm_kernel<T, E, G, CsrTune<E, G>::UNROLL, CsrTune<E, G>::MIN_BLOCKS, CsrTune<E, G>::R,
+                                  CsrTune<E, G>::D>;
     static int blocks_per_sm = 0;   // per instantiation
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kCsrThreads, 0);

@@ -85,11 +85,15 @@ __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, unsigned l
     return r;
 }
 
-template <typename T, int E, int G, int UNROLL>
+// R = index entries held per lane per batch (a batch is 32*R nonzeros), D = batches prefetched ahead.
+template <typename T, int E, int G, int UNROLL, int R, int D>
 __device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrItem &item) {
     using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
     constexpr int P = 32 / G;
+    constexpr int BATCH = 32 * R;
+    constexpr int STEPS = G * R;                 // gather steps per full batch (P nonzeros each)
+    constexpr int U = (UNROLL < STEPS) ? UNROLL : STEPS;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int sub = lane / G;
@@ -102,52 +106,70 @@ __device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrI
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
 
-    // index/value stream, prefetched two batches (64 nonzeros) ahead of the gathers
-    int c0 = 0, c1 = 0;
-    Shfl v0 = 0, v1 = 0;
-    {
-        const int i0 = item.start + lane, i1 = item.start + 32 + lane;
-        if (i0 < end) { c0 = ld_stream(a.colind + i0); v0 = ld_stream(a.val + i0); }
-        if (i1 < end) { c1 = ld_stream(a.colind + i1); v1 = ld_stream(a.val + i1); }
+    // index/value stream, prefetched D batches ahead of the gathers (evict-first: read once)
+    int nc[D][R];
+    Shfl nv[D][R];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = item.start + d * BATCH + r * 32 + lane;
+            nc[d][r] = 0;
+            nv[d][r] = 0;
+            if (i < end) { nc[d][r] = ld_stream(a.colind + i); nv[d][r] = ld_stream(a.val + i); }
+        }
     }
-    for (int base = item.start; base < end; base += 32) {
-        const int c = c0;
-        const Shfl v = v0;
-        c0 = c1;
-        v0 = v1;
-        c1 = 0;
-        v1 = 0;
-        {
-            const int i2 = base + 64 + lane;
-            if (i2 < end) { c1 = ld_stream(a.colind + i2); v1 = ld_stream(a.val + i2); }
+    for (int base = item.start; base < end; base += BATCH) {
+        int c[R];
+        Shfl v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { c[r] = nc[0][r]; v[r] = nv[0][r]; }
+#pragma unroll
+        for (int d = 0; d + 1 < D; ++d) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) { nc[d][r] = nc[d + 1][r]; nv[d][r] = nv[d + 1][r]; }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = base + D * BATCH + r * 32 + lane;
+            nc[D - 1][r] = 0;
+            nv[D - 1][r] = 0;
+            if (i < end) { nc[D - 1][r] = ld_stream(a.colind + i); nv[D - 1][r] = ld_stream(a.val + i); }
         }
         const int rem = end - base;
-        if (rem >= 32) {
-            // full batch: G steps of P nonzeros, UNROLL gathers in flight per lane
+        if (rem >= BATCH) {
+            // full batch: STEPS steps of P nonzeros, U gathers in flight per lane.
+            // step s covers batch entries s*P .. s*P+P-1 = register s/G, source lane (s%G)*P + sub
 #pragma unroll
-            for (int s0 = 0; s0 < G; s0 += UNROLL) {
-                Pack<T, E> b[UNROLL];
+            for (int s0 = 0; s0 < STEPS; s0 += U) {
+                Pack<T, E> b[U];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const int cc = __shfl_sync(FULL, c, (s0 + u) * P + sub);
+                for (int u = 0; u < U; ++u) {
+                    const int cc = __shfl_sync(FULL, c[(s0 + u) / G], ((s0 + u) % G) * P + sub);
                     if (active) b[u] = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
                 }
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const Shfl vv = __shfl_sync(FULL, v, (s0 + u) * P + sub);
+                for (int u = 0; u < U; ++u) {
+                    const Shfl vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
                     if (active) fma_pack<T, E>(acc, b[u], vv);
                 }
             }
         } else {
             // tail batch: per-lane predicate so padded slots never touch B (0 * inf would poison a row)
-            const int steps = (rem + P - 1) / P;
-            for (int s = 0; s < steps; ++s) {
-                const int src = s * P + sub;
-                const int cc = __shfl_sync(FULL, c, src);
-                const Shfl vv = __shfl_sync(FULL, v, src);
-                if (active && src < rem) {
-                    Pack<T, E> b = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
-                    fma_pack<T, E>(acc, b, vv);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int left = rem - r * 32;          // entries of register r that are real
+                if (left > 0) {
+                    const int steps = (min(left, 32) + P - 1) / P;
+                    for (int s = 0; s < steps; ++s) {
+                        const int src = s * P + sub;
+                        const int cc = __shfl_sync(FULL, c[r], src);
+                        const Shfl vv = __shfl_sync(FULL, v[r], src);
+                        if (active && src < left) {
+                            Pack<T, E> b = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+                            fma_pack<T, E>(acc, b, vv);
+                        }
+                    }
                 }
             }
         }
@@ -172,7 +194,7 @@ __device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrI
 
 // Persistent grid: gridDim.x = resident blocks of the device.  Tickets run over
 // col_chunks * (n_seg + nrows) items, column chunk outermost.
-template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS>
+template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D>
 __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const CsrArgs<T> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -193,7 +215,7 @@ __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const
         const unsigned long long nit = take_ticket();
         CsrItem nxt;
         if (nit < total) nxt = csr_load_item<T, G>(a, nit);
-        if (!cur.skip) csr_process_item<T, E, G, UNROLL>(a, cur);
+        if (!cur.skip) csr_process_item<T, E, G, UNROLL, R, D>(a, cur);
         it = nit;
         cur = nxt;
     }
