@@ -3,7 +3,7 @@ kernel parameters from graph statistics instead of UPMEM bandwidth tables.  [fir
 from __future__ import annotations
 
 
-def choose_ds_parts(n_cols: int, hidden: int, elem_size: int, l2_bytes: int, l2_fraction: float = 0.35) -> int:
+def choose_ds_parts(n_cols: int, hidden: int, elem_size: int, l2_bytes: int, l2_fraction: float = 0.46) -> int:
     """Smallest number of equal column tiles for which one B tile (n_cols x hidden/ds x elem_size) fits in
     `l2_fraction` of L2.  B200's L2 is two die-local halves and read-shared data ends up in both, so the
     budget for the resident tile is well below the nominal 126 MB; the streaming A/C traffic needs room too.
