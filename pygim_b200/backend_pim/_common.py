@@ -69,7 +69,7 @@ def edge_values(item, dtype: torch.dtype) -> torch.Tensor:
 def coalesce(row: torch.Tensor, col: torch.Tensor, value: torch.Tensor, ncols: int
              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Sort row-major and sum duplicate (row, col) entries in the value dtype (wrapping for ints),
-    i.e. torch.sparse_coo_tensor(...).coalesce() without building a sparse tensor."""
+    i.e. what coalescing a sparse COO tensor does, without building a sparse tensor."""
     if row.numel() == 0:
         return row, col, value
     key = row.to(torch.int64) * max(int(ncols), 1) + col.to(torch.int64)

@@ -616,10 +616,12 @@ PYGIM_API int pygim_partition_rows_by_nnz(const int32_t *rowptr, int64_t nrows, 
     long long r = 0;
     for (int p = 1; p < nparts; ++p) {
         const long long target = (nnz * p + nparts - 1) / nparts;
-        // first row boundary whose prefix reaches the target
+        // row boundary whose prefix nnz is nearest to the target (never before the previous cut)
         const int32_t *it = std::lower_bound(rowptr + r, rowptr + nrows + 1, target,
                                              [](int32_t a, long long t) { return (long long)(unsigned)a < t; });
-        r = std::min<long long>(it - rowptr, nrows);
+        long long hi = std::min<long long>(it - rowptr, nrows);
+        if (hi > r && target - (long long)(unsigned)rowptr[hi - 1] <= (long long)(unsigned)rowptr[hi] - target) --hi;
+        r = hi;
         split_out[p] = r;
     }
     split_out[nparts] = nrows;
