@@ -72,7 +72,12 @@ def lib(path: Optional[str] = None) -> C.CDLL:
 
 
 def max_threads() -> int:
-    return int(lib().oracle_max_threads())
+    """Host threads available to this process.  Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently serialise the CPU baseline."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def _p(a: Optional[np.ndarray]):

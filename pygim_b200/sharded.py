@@ -96,6 +96,12 @@ class ShardedSpMM:
             all_gather_rows(out, self.row_counts, mine, self.group)
         return out if gather else mine
 
+    def mul_gather_only(self, out: torch.Tensor) -> torch.Tensor:
+        """The collective half of `mul` on its own (lets a caller time compute and all-gather apart)."""
+        if self.world > 1:
+            all_gather_rows(out, self.row_counts, out[self.r0:self.r1], self.group)
+        return out
+
     def free(self):
         if hasattr(self.local, "free"):
             self.local.free()

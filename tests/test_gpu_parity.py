@@ -105,3 +105,24 @@ def test_empty_matrix_and_empty_rows(gpu_backend, oracle):
     for fmt in ("CSR", "COO"):
         out = _run("spmm", adj, make_args(torch.float32, fmt, 16), x)
         assert torch.equal(out, torch.zeros(50, 16))
+
+
+def test_sharded_single_rank_and_reddit_like(gpu_backend, oracle):
+    """ShardedSpMM with world == 1 is the plain plan; checked on a skewed Reddit-like graph (long rows are
+    segmented, the persistent kernel's ticket counter is reused across calls)."""
+    import types
+    from pygim_b200 import graphgen
+    from pygim_b200.sharded import ShardedSpMM
+    adj = graphgen.synthetic_adj("reddit", scale=0.01, seed=2)
+    rowptr, col, _ = adj.csr()
+    n = adj.size(0)
+    for dtype, hidden in ((torch.float32, 32), (torch.float32, 128), (torch.int8, 64), (torch.float64, 16)):
+        args = types.SimpleNamespace(data_type=dtype, sp_format="CSR", hidden_size=hidden, sp_parts=1, ds_parts=1)
+        op = ShardedSpMM(adj.to("cuda"), args)
+        x = graphgen.reference_features(n, hidden, dtype, seed=3)
+        want = oracle.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy())
+        for _ in range(3):                       # repeated launches on one plan
+            got = op.mul(x.cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want), (dtype, hidden)
+        op.free()
