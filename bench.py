@@ -40,9 +40,11 @@ METRIC = "spmm_gflops"
 UNIT = "GFLOP/s"
 
 
-def alg_bytes_csr(n_rows, n_cols, nnz, hidden, s=4):
-    """ALGORITHMIC bytes of one CSR SpMM: rowptr + colind + values + B once + C once."""
-    return 4 * (n_rows + 1) + 4 * nnz + s * nnz + s * n_cols * hidden + s * n_rows * hidden
+def alg_bytes_csr(n_rows, n_cols, nnz, hidden, s=4, fmt="CSR"):
+    """ALGORITHMIC bytes of one SpMM: row index (rowptr | rowind) + colind + values + B once +
+    C once."""
+    row_index = 4 * (n_rows + 1) if fmt == "CSR" else 4 * nnz
+    return row_index + 4 * nnz + s * nnz + s * n_cols * hidden + s * n_rows * hidden
 
 
 def measured_peaks():
@@ -112,8 +114,8 @@ def auto_ds_parts(n_cols, hidden, info, s=4):
     return autotuner.choose_ds_parts(n_cols, hidden, s, info["l2_bytes"])
 
 
-def make_args(hidden, dtype):
-    return types.SimpleNamespace(data_type=dtype, sp_format="CSR", hidden_size=hidden, sp_parts=1, ds_parts=1)
+def make_args(hidden, dtype, fmt="CSR"):
+    return types.SimpleNamespace(data_type=dtype, sp_format=fmt, hidden_size=hidden, sp_parts=1, ds_parts=1)
 
 
 # ====================================================================================== CPU arms
@@ -126,7 +128,7 @@ def cpu_spmm_sample(O, clib, rowptr, col, x_by_h, threads, repeats=1):
     for _ in range(repeats):
         t0 = time.perf_counter()
         for h, x in x_by_h.items():
-            out = np.empty((rowptr.shape[0] - 1, h), dtype=np.float32)
+            out = np.empty((rowptr.shape[0] - 1, h), dtype=x.dtype)
             O.spmm_csr_rowpar(rowptr, col, None, x, nthreads=threads, out=out, clib=clib)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
@@ -202,7 +204,9 @@ def run_ours(a):
     from pygim_b200.backend_pim.spmm import SparseTensorCOO
     from pygim_b200.sparse_tensor import SparseTensor
 
-    dtype = torch.float32
+    from pygim_b200.backend_pim.spmm import TORCH_TYPES
+    dtype = TORCH_TYPES[a.dtype]
+    esize = torch.empty((), dtype=dtype).element_size()
     n, nnz, max_deg = graphgen.SHAPES[a.shape]
     sweep = a.hidden if a.hidden else HIDDEN_SWEEP
     pim_ops.dpu_init_ranks(1)
@@ -218,32 +222,40 @@ def run_ours(a):
     shard_nnz = int(col.numel())
     adj = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(r1 - r0, n), is_sorted=True)
     del rowptr, col
-    base = SparseTensorCOO(adj, dtype=dtype, format="CSR")
-    base.build_csr()
-    plans = {}
-    for h in sweep:
-        A = copy.copy(base)          # shares the int32 CSR arrays; one plan per hidden size
-        A.sp_info_ptr = None
-        A.to_pim_group(h, a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, info))
-        plans[h] = A
+    from pygim_b200.sharded import ShardedSpMM
+    ds_parts = {h: (a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, info, esize)) for h in sweep}
+
+    def args_for(h):
+        ns = make_args(h, dtype, a.format)
+        ns.ds_parts = ds_parts[h]
+        return ns
+
+    if world == 1:
+        # one set of int32 CSR/COO arrays shared by the four plans (one plan per hidden size)
+        base = SparseTensorCOO(adj, dtype=dtype, format=a.format)
+        base.build_csr() if a.format == "CSR" else base.build_coo()
+        plans = {}
+        for h in sweep:
+            A = copy.copy(base)
+            A.sp_info_ptr = None
+            A.to_pim_group(h, ds_parts[h])
+            plans[h] = A
+        ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj,
+                              make_local=lambda _adj, _args, _h=h: plans[_h]) for h in sweep}
+    else:
+        ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj, chunks=a.chunks) for h in sweep}
+        plans = {h: ops[h].locals[0] for h in sweep}
     x_dev = {h: graphgen.reference_features(n, h, dtype, seed=h, device=str(dev)) for h in sweep}
     # full outputs (every rank ends with all rows, ready for the next layer)
     c_full = {h: torch.empty((n, h), dtype=dtype, device=dev) for h in sweep}
-    row_counts = [splits[i + 1] - splits[i] for i in range(world)]
-
-    from pygim_b200.sharded import ShardedSpMM
-    ops = {h: ShardedSpMM(None, make_args(h, dtype), splits=splits, local_adj=adj,
-                          make_local=lambda _adj, _args, _h=h: plans[_h]) for h in sweep}
 
     def step_device(record=None):
         for i, h in enumerate(sweep):
             if record is not None:
                 record[i][0].record()
-            ops[h].mul(x_dev[h], out=c_full[h], gather=False)          # this rank's row block, in place
+            ops[h].mul(x_dev[h], out=c_full[h])        # N > 1: SpMM of the row block(s) + all-gather
             if record is not None:
                 record[i][1].record()
-            if world > 1:                                              # all-gather of the unequal row blocks
-                ops[h].mul_gather_only(c_full[h])
 
     def sync():
         torch.cuda.synchronize()
@@ -267,7 +279,7 @@ def run_ours(a):
     t_end.record()
     sync()
     elapsed_ms = t_begin.elapsed_time(t_end)
-    launches_per_step = sum(pim_ops.last_launches(plans[h].sp_info_ptr) for h in sweep)
+    launches_per_step = sum(pim_ops.last_launches(op.sp_info_ptr) for h in sweep for op in ops[h].locals)
     per_h_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(a.steps)) / a.steps
                 for i in range(len(sweep))]
     if world > 1:
@@ -285,7 +297,12 @@ def run_ours(a):
 
     def step_host():
         for h in sweep:
-            plans[h].mul(x_host[h], out=c_host[h])
+            if world == 1:
+                plans[h].mul(x_host[h], out=c_host[h])
+            else:   # each rank's row block(s) through the host entry point; no collective on host results
+                blk = ops[h]
+                for k, op in enumerate(blk.locals):
+                    op.mul(x_host[h], out=c_host[h][blk.sub[k]:blk.sub[k + 1]])
 
     e2e_steps = max(3, min(a.steps, 10)) if not a.no_e2e else 1
     for _ in range(2 if not a.no_e2e else 0):
@@ -301,8 +318,8 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_value = flops_step * e2e_steps / e2e_s / 1e9
-    h2d = sum(n * h * 4 for h in sweep)
-    d2h = sum((r1 - r0) * h * 4 for h in sweep)
+    h2d = sum(n * h * esize for h in sweep)
+    d2h = sum((r1 - r0) * h * esize for h in sweep)
     timers = {h: pim_ops.last_timers(plans[h].sp_info_ptr) for h in sweep}
 
     # ---- parity spot check of what was just timed (rank 0, first rows, against the oracle)
@@ -317,7 +334,7 @@ def run_ours(a):
         cl_h = cl[: int(rp_h[-1])].cpu().numpy().astype("int32")
         parity = True
         for h in sweep:
-            want = O.spmm_csr_rowpar(rp_h, cl_h, None, x_host[h].numpy())
+            want = O.spmm_csr_rowpar(rp_h, cl_h, None, x_host[h].numpy(), nthreads=O.max_threads())
             parity = parity and bool(np.array_equal(want, c_full[h][r0:r0 + rows_chk].cpu().numpy())) \
                 and bool(np.array_equal(want, c_host[h][:rows_chk].numpy()))
 
@@ -332,18 +349,19 @@ def run_ours(a):
     per_hidden = []
     for i, h in enumerate(sweep):
         # per-GPU algorithmic bytes of this rank's launch (shard of A and C, all of B)
-        b = alg_bytes_csr(r1 - r0, n, shard_nnz, h)
+        b = alg_bytes_csr(r1 - r0, n, shard_nnz, h, esize, a.format)
         per_hidden.append({"hidden": h, "kernel_ms": per_h_ms[i], "gflops": 2.0 * shard_nnz * h / per_h_ms[i] / 1e6,
                            "alg_gbs": b / per_h_ms[i] / 1e6, "frac_hbm": b / per_h_ms[i] / 1e6 / peak,
-                           "gather_gbs": 4.0 * shard_nnz * h / per_h_ms[i] / 1e6})
-    roof = {"bound": "hbm", "kernel": "csr_spmm_kernel<float,4,%d> (hidden %d)" % (min(32, sweep[dom] // 4), sweep[dom]),
+                           "gather_gbs": float(esize) * shard_nnz * h / per_h_ms[i] / 1e6})
+    roof = {"bound": "hbm", "kernel": "%s_spmm_kernel<%s> (hidden %d)" % (a.format.lower(), a.dtype, sweep[dom]),
             "achieved": per_hidden[dom]["alg_gbs"], "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": per_hidden[dom]["frac_hbm"], "traffic": None,
-            "alg_bytes_per_launch": alg_bytes_csr(r1 - r0, n, shard_nnz, sweep[dom]),
-            "sweep_achieved": sum(alg_bytes_csr(r1 - r0, n, shard_nnz, h) for h in sweep) / sum(per_h_ms) / 1e6,
+            "alg_bytes_per_launch": alg_bytes_csr(r1 - r0, n, shard_nnz, sweep[dom], esize, a.format),
+            "sweep_achieved": sum(alg_bytes_csr(r1 - r0, n, shard_nnz, h, esize, a.format) for h in sweep)
+            / sum(per_h_ms) / 1e6,
             "note": "Reddit-shape is L2-gather bound (s*nnz*H bytes leave L2 per launch), see DESIGN.md"}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_path):
+    if os.path.exists(traffic_path) and (a.shape, a.dtype, a.format, world) == ("reddit", "FLT32", "CSR", 1):
         try:
             with open(traffic_path) as f:
                 roof["traffic"] = json.load(f).get(str(sweep[dom]))
@@ -371,11 +389,14 @@ def run_ours(a):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s-shape FLT32 CSR SpMM, hidden sweep %s" % (a.shape, "/".join(map(str, sweep))),
-                   "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": "CSR", "sp_parts": 1,
-                   "ds_parts": {str(h): plans[h].dense_parts for h in sweep},
-                   "sharding": "rows by nnz over %d GPU(s), B replicated, NCCL all-gather of C inside the timing" % world
+        "dtype": {"FLT32": "f32", "DBL64": "f64", "INT8": "i8", "INT16": "i16", "INT32": "i32", "INT64": "i64"}[a.dtype],
+        "data": "synthetic",
+        "config": {"workload": "%s-shape %s %s SpMM, hidden sweep %s" % (a.shape, a.dtype, a.format,
+                                                                         "/".join(map(str, sweep))),
+                   "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": a.format, "sp_parts": 1,
+                   "ds_parts": {str(h): ds_parts[h] for h in sweep},
+                   "sharding": "rows by nnz over %d GPUs, B replicated, %d sub-blocks per rank, NCCL all-gather of C "
+                               "inside the timing (overlapped with the next sub-block's SpMM)" % (world, a.chunks)
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (A = %.0f MB streams through a %.0f MB L2 every launch)"
                          % ((8.0 * nnz) / 1e6, info["l2_bytes"] / 1e6)},
@@ -400,11 +421,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default=SHAPE, choices=["reddit", "products", "arxiv"])
     ap.add_argument("--hidden", type=int, nargs="*", default=None, help="override the hidden sweep")
+    ap.add_argument("--dtype", default="FLT32", choices=["INT8", "INT16", "INT32", "INT64", "FLT32", "DBL64"])
+    ap.add_argument("--format", default="CSR", choices=["CSR", "COO"])
     ap.add_argument("--cpu-sample-rows", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: one untimed-quality e2e pass only")
     ap.add_argument("--ds-parts", type=int, default=0, help="dense column parts per launch group; 0 = automatic")
+    ap.add_argument("--chunks", type=int, default=1, help="N > 1: sub-blocks per rank (all-gather/compute overlap)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

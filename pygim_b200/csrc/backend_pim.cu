@@ -114,7 +114,7 @@ struct Group {
     std::vector<SparsePart> parts;
     std::vector<long long> dense_cols;
     // options (< 0 = automatic)
-    long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1;
+    long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1, opt_rows_per_ticket = -1;
     // dynamic work distribution of the persistent CSR kernel: a device ticket counter that only grows
     unsigned long long *d_ticket = nullptr;
     unsigned long long ticket_base = 0;
@@ -267,6 +267,11 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.n_long = p.n_long;
         l.nrows = (int)p.nrows;
         l.seg_len = p.seg_len;
+        // ~256 nonzeros per ticket: one row on Reddit-like graphs, 10 on products-like, 31 on citation graphs
+        l.rows_per_ticket = g->opt_rows_per_ticket > 0
+                                ? (int)g->opt_rows_per_ticket
+                                : (int)std::max<long long>(1, std::min<long long>(31, 256 * std::max<long long>(p.nrows, 1) /
+                                                                                     std::max<long long>(p.nnz, 1)));
         l.ncols = width;
         l.ldb = ldb;
         l.ldc = ldc;
@@ -292,6 +297,9 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.chunk_nnz = (int)g->opt_chunk_nnz;
         l.accumulate = accumulate ? 1 : 0;
         l.n_warp_slots = g_ctx.sm_count * (g_ctx.max_threads_per_sm / 32);
+        l.sm_count = g_ctx.sm_count;
+        l.ticket = g->d_ticket;
+        l.ticket_base = &g->ticket_base;
         l.stream = stream;
         err = dispatch_coo(g->dtype, l, &g->last_launches);
     }
@@ -497,6 +505,8 @@ PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int6
         g->opt_l2_persist = value;
     } else if (!std::strcmp(key, "chunk_nnz")) {
         g->opt_chunk_nnz = value;
+    } else if (!std::strcmp(key, "rows_per_ticket")) {
+        g->opt_rows_per_ticket = value;
     } else {
         return fail(PYGIM_ERR_INVALID, "unknown option '%s'", key);
     }

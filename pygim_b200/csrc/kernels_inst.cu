@@ -44,12 +44,22 @@ static int pow2_ceil(long long v) {
 #ifndef PYGIM_CSR_PREFETCH
 #define PYGIM_CSR_PREFETCH 2
 #endif
+#ifndef PYGIM_NARROW_UNROLL
+#define PYGIM_NARROW_UNROLL 4
+#endif
+#ifndef PYGIM_NARROW_MINBLOCKS
+#define PYGIM_NARROW_MINBLOCKS 2
+#endif
+// 8/16-bit types carry E = 16/8 32-bit accumulators per lane: fewer gathers in flight and a larger register
+// budget keep those instantiations spill-free.
 template <int E, int G> struct CsrTune {
-    static constexpr int UNROLL = PYGIM_CSR_UNROLL;
+    static constexpr int UNROLL = (E >= 8) ? PYGIM_NARROW_UNROLL : PYGIM_CSR_UNROLL;
     static constexpr int R = (G >= UNROLL) ? 1 : ((UNROLL / G) > 4 ? 4 : (UNROLL / G));
     static constexpr int D = (R > 1) ? 1 : PYGIM_CSR_PREFETCH;
-    static constexpr int MIN_BLOCKS = (sizeof(T) * E >= 16) ? PYGIM_CSR_MINBLOCKS : 4;
+    static constexpr int MIN_BLOCKS =
+        (E >= 8) ? PYGIM_NARROW_MINBLOCKS : ((sizeof(T) * E >= 16) ? PYGIM_CSR_MINBLOCKS : 4);
 };
+template <int E, int G> using CooTune = CsrTune<E, G>;   // COO adds a third index stream; same budget works
 
 template <int E, int G> static cudaError_t launch_csr_g(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
     auto kernel = csr_spmm_kernel<T, E, G, CsrTune<E, G>::UNROLL, CsrTune<E, G>::MIN_BLOCKS, CsrTune<E, G>::R,
@@ -61,7 +71,8 @@ template <int E, int G> static cudaError_t launch_csr_g(CsrArgs<T> a, const CsrL
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     a.col_chunks = (a.nvec + G - 1) / G;
-    const unsigned long long total = (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + a.nrows);
+    const unsigned long long total =
+        (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + (unsigned long long)a.n_row_tickets);
     const unsigned long long warps_needed = total;
     unsigned long long blocks = (unsigned long long)blocks_per_sm * (l.sm_count > 0 ? l.sm_count : 148);
     const unsigned long long blocks_needed = (warps_needed + (kCsrThreads / 32) - 1) / (kCsrThreads / 32);
@@ -87,6 +98,8 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.n_seg = l.n_seg;
     a.nrows = l.nrows;
     a.seg_len = l.seg_len;
+    a.rows_per_ticket = l.rows_per_ticket < 1 ? 1 : (l.rows_per_ticket > 31 ? 31 : l.rows_per_ticket);
+    a.n_row_tickets = (l.nrows + a.rows_per_ticket - 1) / a.rows_per_ticket;
     a.nvec = (int)(l.ncols / E);
     a.ldb = l.ldb;
     a.ldc = l.ldc;
@@ -127,6 +140,28 @@ cudaError_t PYGIM_CAT(launch_csr_, PYGIM_SFX)(const CsrLaunch &l, int64_t *launc
     return launch_csr_e<1>(l, launches);
 }
 
+template <int E, int G> static cudaError_t launch_coo_g(CooArgs<T> a, const CooLaunch &l, int64_t *launches) {
+    auto kernel = coo_spmm_kernel<T, E, G, CooTune<E, G>::UNROLL, CooTune<E, G>::MIN_BLOCKS, CooTune<E, G>::R,
+                                  CooTune<E, G>::D>;
+    static int blocks_per_sm = 0;   // per instantiation
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kCooThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    a.col_chunks = (a.nvec + G - 1) / G;
+    const unsigned long long total = (unsigned long long)a.col_chunks * (unsigned long long)a.n_chunks;
+    unsigned long long blocks = (unsigned long long)blocks_per_sm * (l.sm_count > 0 ? l.sm_count : 148);
+    const unsigned long long blocks_needed = (total + (kCooThreads / 32) - 1) / (kCooThreads / 32);
+    if (blocks > blocks_needed) blocks = blocks_needed;
+    a.ticket = l.ticket;
+    a.ticket_base = *l.ticket_base;
+    kernel<<<(unsigned)blocks, kCooThreads, 0, l.stream>>>(a);
+    *l.ticket_base += total + blocks * (kCooThreads / 32);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *launches) {
     CooArgs<T> a;
     a.rowind = l.rowind;
@@ -148,32 +183,24 @@ template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *la
         ++*launches;
     }
     if (l.nnz == 0 || a.nvec == 0) return cudaSuccess;
-    const int G = pow2_ceil(a.nvec);
-    const int P = 32 / G;
-    // exact equal-nnz chunks (BLNC_NNZ): aim at ~8 chunks per resident warp, 64..2048 nonzeros each
+    // exact equal-nnz chunks (BLNC_NNZ): ~8 chunks per resident warp, 256..4096 nonzeros each, multiple of 32
     long long chunk = l.chunk_nnz;
     if (chunk <= 0) {
-        chunk = l.nnz / ((long long)(l.n_warp_slots > 0 ? l.n_warp_slots : 9472) * 8);
-        if (chunk < 64) chunk = 64;
-        if (chunk > 2048) chunk = 2048;
+        const long long want = l.nnz / ((long long)(l.n_warp_slots > 0 ? l.n_warp_slots : 9472) * 8);
+        chunk = 256;
+        while (chunk < want && chunk < 4096) chunk <<= 1;
     }
-    long long sub = (chunk + P - 1) / P;
-    sub = (sub + G - 1) / G * G;
-    a.sub_nnz = (int)sub;
-    const long long per_warp = sub * P;
-    const long long warps = (l.nnz + per_warp - 1) / per_warp;
-    dim3 grid((unsigned)((warps + kCooWarpsPerBlock - 1) / kCooWarpsPerBlock), (unsigned)((a.nvec + G - 1) / G));
-    dim3 block(kCooWarpsPerBlock * 32);
-    switch (G) {
-        case 1: coo_spmm_kernel<T, E, 1><<<grid, block, 0, l.stream>>>(a); break;
-        case 2: coo_spmm_kernel<T, E, 2><<<grid, block, 0, l.stream>>>(a); break;
-        case 4: coo_spmm_kernel<T, E, 4><<<grid, block, 0, l.stream>>>(a); break;
-        case 8: coo_spmm_kernel<T, E, 8><<<grid, block, 0, l.stream>>>(a); break;
-        case 16: coo_spmm_kernel<T, E, 16><<<grid, block, 0, l.stream>>>(a); break;
-        default: coo_spmm_kernel<T, E, 32><<<grid, block, 0, l.stream>>>(a); break;
+    chunk = (chunk + 31) / 32 * 32;
+    a.chunk_nnz = (int)chunk;
+    a.n_chunks = (l.nnz + chunk - 1) / chunk;
+    switch (pow2_ceil(a.nvec)) {
+        case 1: return launch_coo_g<E, 1>(a, l, launches);
+        case 2: return launch_coo_g<E, 2>(a, l, launches);
+        case 4: return launch_coo_g<E, 4>(a, l, launches);
+        case 8: return launch_coo_g<E, 8>(a, l, launches);
+        case 16: return launch_coo_g<E, 16>(a, l, launches);
+        default: return launch_coo_g<E, 32>(a, l, launches);
     }
-    ++*launches;
-    return cudaGetLastError();
 }
 
 cudaError_t PYGIM_CAT(launch_coo_, PYGIM_SFX)(const CooLaunch &l, int64_t *launches) {

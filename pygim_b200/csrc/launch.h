@@ -19,6 +19,7 @@ struct CsrLaunch {
     const int *long_rows;
     const int *long_seg_ptr;
     int n_seg, n_long, nrows, seg_len;
+    int rows_per_ticket;      // consecutive rows one work ticket covers (short-row graphs)
     long long ncols;          // dense columns of this tile
     long long ldb, ldc, ldp;  // row strides in elements
     int accumulate;
@@ -39,6 +40,9 @@ struct CooLaunch {
     int chunk_nnz;            // target nonzeros per warp; <= 0 = automatic
     int accumulate;           // 0: the launcher zero-fills the C tile first
     int n_warp_slots;         // resident warps of the device (for the automatic chunk size)
+    int sm_count;
+    unsigned long long *ticket;
+    unsigned long long *ticket_base;
     cudaStream_t stream;
 };
 

@@ -8,17 +8,21 @@
 // tasklet adds up afterwards (LOCKFREE / LOCKFREEV2, spmm_mul_coo_dpu.c:166-390) plus a host-side
 // add of the DPU boundary rows (spmm_mul_coo.c:478-489).  Here:
 //
-//  * a warp owns chunk_nnz consecutive nonzeros, split into P = 32/G contiguous sub-chunks, one
-//    per group of G lanes (G lanes x 16 bytes cover one dense row);
-//  * each group streams its sub-chunk - G (row, col, val) triples per coalesced load, handed
-//    round the group with width-G shuffles - and runs a segmented reduction in registers:
-//    the accumulator is flushed whenever the row index changes;
-//  * rows that lie wholly inside one sub-chunk are written with plain stores; only a sub-chunk's
-//    first/last row, and only if the neighbouring nonzero really has the same row, is combined
-//    with atomics (integer atomics are exact; float atomics commute up to rounding - see DESIGN.md).
+//  * the grid is persistent; warps draw chunks of chunk_nnz consecutive nonzeros from a ticket
+//    counter (same scheme as the CSR kernel);
+//  * a warp streams its chunk 32*R triples (row, col, val) at a time - coalesced evict-first
+//    loads, prefetched D batches ahead.  If the whole batch belongs to the row being accumulated
+//    (the common case on dense-ish graphs) it is gathered exactly like a CSR batch: G lanes x 16
+//    bytes per dense row, P = 32/G nonzeros per load instruction, UNROLL gathers in flight;
+//  * otherwise the batch is walked run by run: row runs are found with a ballot over the row
+//    stream, and at every row change the P interleaved partial sums are combined by the same
+//    fixed xor-shuffle tree and flushed - a segmented reduction in registers and shuffles;
+//  * rows that lie wholly inside a chunk are written with plain stores; only a chunk's first /
+//    last row, and only if the neighbouring nonzero really has the same row, is combined with
+//    atomics (integer atomics are exact; float atomics commute up to rounding - see DESIGN.md).
 //
-// C is zero-filled by the caller before the launch (the reference's torch::zeros,
-// pytorch_api.cpp:357-358) unless accumulate is set.
+// C is zero-filled by the launcher first (the reference's torch::zeros, pytorch_api.cpp:357-358)
+// unless accumulate is set.
 #pragma once
 #include "vec.cuh"
 
@@ -30,14 +34,18 @@ template <typename T> struct CooArgs {
     const T *val;
     const T *B;
     T *C;
+    unsigned long long *ticket;
+    unsigned long long ticket_base;
     long long nnz;
+    long long n_chunks;
     long long ldb, ldc;
-    int sub_nnz;       // nonzeros per sub-chunk (multiple of G); a warp covers P * sub_nnz
+    int chunk_nnz;     // nonzeros per work item (multiple of 32)
     int nvec;          // words (of E elements) per dense row
+    int col_chunks;    // ceil(nvec / G)
     int accumulate;
 };
 
-constexpr int kCooWarpsPerBlock = 8;
+constexpr int kCooThreads = 256;
 
 template <typename T> __device__ __forceinline__ void atomic_add_elem(T *p, typename Arith<T>::Acc v) {
     if constexpr (std::is_same<T, float>::value || std::is_same<T, double>::value) {
@@ -61,95 +69,155 @@ template <typename T> __device__ __forceinline__ void atomic_add_elem(T *p, type
     }
 }
 
-template <typename T, int E>
-__device__ __forceinline__ void coo_flush(T *dst, typename Arith<T>::Acc (&acc)[E], bool exclusive, bool accumulate) {
-    if (exclusive) {
-        if (accumulate) add_old<T, E>(acc, ld_plain<T, E>(dst));
-        st_plain<T, E>(dst, narrow<T, E>(acc));
-    } else {
+// Combine the P interleaved partial sums (all lanes take part) and write / add the row.
+template <typename T, int E, int G>
+__device__ __forceinline__ void coo_flush_row(T *Crow, typename Arith<T>::Acc (&acc)[E], bool writer, bool exclusive,
+                                              bool accumulate) {
+    using Acc = typename Arith<T>::Acc;
+    constexpr unsigned FULL = 0xffffffffu;
 #pragma unroll
-        for (int k = 0; k < E; ++k) atomic_add_elem<T>(dst + k, acc[k]);
+    for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
     }
+    if (writer) {
+        if (exclusive) {
+            if (accumulate) add_old<T, E>(acc, ld_plain<T, E>(Crow));
+            st_plain<T, E>(Crow, narrow<T, E>(acc));
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; ++k) atomic_add_elem<T>(Crow + k, acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
 }
 
-// grid.x = ceil(n_chunks / kCooWarpsPerBlock); grid.y = column chunks of G words (only > 1 when G == 32)
-template <typename T, int E, int G>
-__global__ void __launch_bounds__(kCooWarpsPerBlock * 32) coo_spmm_kernel(const CooArgs<T> a) {
+template <typename T, int E, int G, int UNROLL, int R, int D>
+__device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long cs, long long ce, int chunk) {
     using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
     constexpr int P = 32 / G;
-    constexpr int UNROLL = (G < 8) ? G : 8;
+    constexpr int BATCH = 32 * R;
+    constexpr int STEPS = G * R;
+    constexpr int U = (UNROLL < STEPS) ? UNROLL : STEPS;
     constexpr unsigned FULL = 0xffffffffu;
-
-    const long long warp = (long long)blockIdx.x * kCooWarpsPerBlock + (threadIdx.x >> 5);
-    const long long chunk_start = warp * (long long)P * a.sub_nnz;
-    if (chunk_start >= a.nnz) return;   // whole warp leaves together
     const int lane = threadIdx.x & 31;
-    const int sub = lane / G, l = lane % G;
-    const int vec = blockIdx.y * G + l;
+    const int sub = lane / G;
+    const int vec = chunk * G + (lane % G);
     const bool active = vec < a.nvec;
+    const bool writer = active && sub == 0;
+    const bool accumulate = a.accumulate != 0;
     const T *Bcol = a.B + (long long)vec * E;
     T *Ccol = a.C + (long long)vec * E;
 
-    long long s_begin = chunk_start + (long long)sub * a.sub_nnz;
-    long long s_end = s_begin + a.sub_nnz;
-    if (s_begin > a.nnz) s_begin = a.nnz;
-    if (s_end > a.nnz) s_end = a.nnz;
-    const bool nonempty = s_begin < s_end;
-
     // does the neighbouring nonzero belong to the same row as our first / last one?
-    int first_row = -1;
-    bool shared_head = false, shared_tail = false;
-    if (nonempty) {
-        first_row = a.rowind[s_begin];
-        shared_head = s_begin > 0 && a.rowind[s_begin - 1] == first_row;
-        shared_tail = s_end < a.nnz && a.rowind[s_end] == a.rowind[s_end - 1];
-    }
+    const int first_row = a.rowind[cs];
+    const bool head_shared = cs > 0 && a.rowind[cs - 1] == first_row;
+    const bool tail_shared = ce < a.nnz && a.rowind[ce] == a.rowind[ce - 1];
 
     Acc acc[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
     int cur = first_row;
 
-    for (int off = 0; off < a.sub_nnz; off += G) {   // uniform trip count across the warp
-        const long long idx = s_begin + off + l;
-        int r = -1, c = 0;
-        Shfl v = 0;
-        if (idx < s_end) {
-            r = ld_stream(a.rowind + idx);
-            c = ld_stream(a.colind + idx);
-            v = ld_stream(a.val + idx);
+    int nr[D][R], nc[D][R];
+    Shfl nv[D][R];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long i = cs + d * BATCH + r * 32 + lane;
+            nr[d][r] = -1; nc[d][r] = 0; nv[d][r] = 0;
+            if (i < ce) { nr[d][r] = ld_stream(a.rowind + i); nc[d][r] = ld_stream(a.colind + i); nv[d][r] = ld_stream(a.val + i); }
+        }
+    }
+    for (long long base = cs; base < ce; base += BATCH) {
+        int rr[R], c[R];
+        Shfl v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { rr[r] = nr[0][r]; c[r] = nc[0][r]; v[r] = nv[0][r]; }
+#pragma unroll
+        for (int d = 0; d + 1 < D; ++d) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) { nr[d][r] = nr[d + 1][r]; nc[d][r] = nc[d + 1][r]; nv[d][r] = nv[d + 1][r]; }
         }
 #pragma unroll
-        for (int j0 = 0; j0 < G; j0 += UNROLL) {
-            Pack<T, E> b[UNROLL];
-            int rr[UNROLL];
-            Shfl vv[UNROLL];
+        for (int r = 0; r < R; ++r) {
+            const long long i = base + (long long)D * BATCH + r * 32 + lane;
+            nr[D - 1][r] = -1; nc[D - 1][r] = 0; nv[D - 1][r] = 0;
+            if (i < ce) { nr[D - 1][r] = ld_stream(a.rowind + i); nc[D - 1][r] = ld_stream(a.colind + i); nv[D - 1][r] = ld_stream(a.val + i); }
+        }
+        const long long rem = ce - base;
+        // whole batch inside the current row?  (sorted stream: first and last entry decide)
+        const int r_first = __shfl_sync(FULL, rr[0], 0);
+        const int r_last = __shfl_sync(FULL, rr[R - 1], 31);
+        if (rem >= BATCH && r_first == cur && r_last == cur) {
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                rr[u] = __shfl_sync(FULL, r, j0 + u, G);
-                const int cc = __shfl_sync(FULL, c, j0 + u, G);
-                vv[u] = __shfl_sync(FULL, v, j0 + u, G);
-                if (active && rr[u] >= 0) b[u] = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+            for (int s0 = 0; s0 < STEPS; s0 += U) {
+                Pack<T, E> b[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int cc = __shfl_sync(FULL, c[(s0 + u) / G], ((s0 + u) % G) * P + sub);
+                    if (active) b[u] = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const Shfl vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
+                    if (active) fma_pack<T, E>(acc, b[u], vv);
+                }
             }
+        } else {
+            // walk the batch run by run (a run = consecutive entries of one row)
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                if (active && rr[u] >= 0) {
-                    if (rr[u] != cur) {
-                        coo_flush<T, E>(Ccol + (long long)cur * a.ldc, acc, !(cur == first_row && shared_head),
-                                        a.accumulate != 0);
-#pragma unroll
-                        for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
-                        cur = rr[u];
+            for (int r = 0; r < R; ++r) {
+                const long long left64 = rem - r * 32;
+                const int left = left64 > 32 ? 32 : (int)left64;       // real entries of register r
+                int pos = 0;
+                while (pos < left) {                                   // warp-uniform
+                    const int row_here = __shfl_sync(FULL, rr[r], pos);
+                    if (row_here != cur) {
+                        coo_flush_row<T, E, G>(Ccol + (long long)cur * a.ldc, acc, writer,
+                                               !(cur == first_row && head_shared), accumulate);
+                        cur = row_here;
                     }
-                    fma_pack<T, E>(acc, b[u], vv[u]);
+                    const unsigned differs = __ballot_sync(FULL, lane >= pos && lane < left && rr[r] != row_here);
+                    const int run_end = differs ? (__ffs(differs) - 1) : left;
+                    for (int s = pos; s < run_end; s += P) {
+                        const int src = s + sub;
+                        const int cc = __shfl_sync(FULL, c[r], src & 31);
+                        const Shfl vv = __shfl_sync(FULL, v[r], src & 31);
+                        if (active && src < run_end) {
+                            Pack<T, E> b = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+                            fma_pack<T, E>(acc, b, vv);
+                        }
+                    }
+                    pos = run_end;
                 }
             }
         }
     }
-    if (active && nonempty) {
-        coo_flush<T, E>(Ccol + (long long)cur * a.ldc, acc, !(cur == first_row && shared_head) && !shared_tail,
-                        a.accumulate != 0);
+    coo_flush_row<T, E, G>(Ccol + (long long)cur * a.ldc, acc, writer,
+                           !(cur == first_row && head_shared) && !tail_shared, accumulate);
+}
+
+// Persistent grid; tickets run over col_chunks * n_chunks items, column chunk outermost.
+template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D>
+__global__ void __launch_bounds__(kCooThreads, MIN_BLOCKS) coo_spmm_kernel(const CooArgs<T> a) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long total = (unsigned long long)a.col_chunks * (unsigned long long)a.n_chunks;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1ULL) - a.ticket_base;
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= total) break;
+        const int chunk = (int)(t / (unsigned long long)a.n_chunks);
+        const long long k = (long long)(t % (unsigned long long)a.n_chunks);
+        const long long cs = k * a.chunk_nnz;
+        long long ce = cs + a.chunk_nnz;
+        if (ce > a.nnz) ce = a.nnz;
+        coo_process_chunk<T, E, G, UNROLL, R, D>(a, cs, ce, chunk);
     }
 }
 

@@ -46,6 +46,8 @@ template <typename T> struct CsrArgs {
     int n_seg;
     int nrows;
     int seg_len;       // rows with more nonzeros than this are handled through segs
+    int rows_per_ticket;   // short-row graphs: a ticket covers this many consecutive rows (1..31)
+    int n_row_tickets;     // ceil(nrows / rows_per_ticket)
     int nvec;          // words (of E elements) per dense row
     int col_chunks;    // ceil(nvec / G): every item is processed once per chunk of G words
     long long ldb, ldc, ldp;
@@ -55,39 +57,40 @@ template <typename T> struct CsrArgs {
 constexpr int kCsrThreads = 256;
 
 struct CsrItem {
-    int start, end;    // nonzero range
-    int row;           // output row (C) or slot (partial)
+    int first;         // segment: slot of the partial buffer; rows: first row of the ticket
+    int count;         // rows covered (1 for a segment)
+    int rp;            // rows: lane l holds rowptr[first + l] (l <= count); segment: lane 0 start, lane 1 end
     int chunk;         // column chunk
     bool to_partial;
-    bool skip;
 };
 
-template <typename T, int G>
+// tickets: col_chunks x (n_seg segment items, then n_row_tickets row groups)
+template <typename T>
 __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, unsigned long long it) {
     CsrItem r;
-    const unsigned long long items = (unsigned long long)a.n_seg + (unsigned long long)a.nrows;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long items = (unsigned long long)a.n_seg + (unsigned long long)a.n_row_tickets;
     r.chunk = (int)(it / items);
     const long long k = (long long)(it % items);
     if (k < a.n_seg) {
         const Seg sg = a.segs[k];
-        r.start = sg.start;
-        r.end = sg.end;
-        r.row = sg.slot;
+        r.first = sg.slot;
+        r.count = 1;
+        r.rp = lane == 0 ? sg.start : sg.end;
         r.to_partial = true;
-        r.skip = false;
     } else {
-        r.row = (int)(k - a.n_seg);
-        r.start = a.rowptr[r.row];
-        r.end = a.rowptr[r.row + 1];
+        r.first = (int)(k - a.n_seg) * a.rows_per_ticket;
+        r.count = min(a.rows_per_ticket, a.nrows - r.first);
+        r.rp = a.rowptr[min(r.first + lane, a.nrows)];
         r.to_partial = false;
-        r.skip = (r.end - r.start) > a.seg_len;   // covered by its segments + fix-up
     }
     return r;
 }
 
 // R = index entries held per lane per batch (a batch is 32*R nonzeros), D = batches prefetched ahead.
 template <typename T, int E, int G, int UNROLL, int R, int D>
-__device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrItem &item) {
+__device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range_start, int range_end, int chunk,
+                                                  int dst_row, bool to_partial) {
     using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
     constexpr int P = 32 / G;
@@ -97,10 +100,10 @@ __device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrI
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int sub = lane / G;
-    const int vec = item.chunk * G + (lane % G);
+    const int vec = chunk * G + (lane % G);
     const bool active = vec < a.nvec;
     const T *Bcol = a.B + (long long)vec * E;
-    const int end = item.end;
+    const int end = range_end;
 
     Acc acc[E];
 #pragma unroll
@@ -113,13 +116,13 @@ __device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrI
     for (int d = 0; d < D; ++d) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = item.start + d * BATCH + r * 32 + lane;
+            const int i = range_start + d * BATCH + r * 32 + lane;
             nc[d][r] = 0;
             nv[d][r] = 0;
             if (i < end) { nc[d][r] = ld_stream(a.colind + i); nv[d][r] = ld_stream(a.val + i); }
         }
     }
-    for (int base = item.start; base < end; base += BATCH) {
+    for (int base = range_start; base < end; base += BATCH) {
         int c[R];
         Shfl v[R];
 #pragma unroll
@@ -182,10 +185,10 @@ __device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrI
         for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
     }
     if (sub == 0 && active) {
-        if (item.to_partial) {
-            st_plain<T, E>(a.partial + (long long)item.row * a.ldp + (long long)vec * E, narrow<T, E>(acc));
+        if (to_partial) {
+            st_plain<T, E>(a.partial + (long long)dst_row * a.ldp + (long long)vec * E, narrow<T, E>(acc));
         } else {
-            T *p = a.C + (long long)item.row * a.ldc + (long long)vec * E;
+            T *p = a.C + (long long)dst_row * a.ldc + (long long)vec * E;
             if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(p));
             st_stream<T, E>(p, narrow<T, E>(acc));
         }
@@ -193,13 +196,13 @@ __device__ __forceinline__ void csr_process_item(const CsrArgs<T> &a, const CsrI
 }
 
 // Persistent grid: gridDim.x = resident blocks of the device.  Tickets run over
-// col_chunks * (n_seg + nrows) items, column chunk outermost.
+// col_chunks * (n_seg + n_row_tickets) items, column chunk outermost.
 template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D>
 __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const CsrArgs<T> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned long long total =
-        (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + (unsigned long long)a.nrows);
+        (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + (unsigned long long)a.n_row_tickets);
 
     auto take_ticket = [&]() -> unsigned long long {
         unsigned long long t = 0;
@@ -209,13 +212,19 @@ __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const
 
     unsigned long long it = take_ticket();
     CsrItem cur;
-    if (it < total) cur = csr_load_item<T, G>(a, it);
+    if (it < total) cur = csr_load_item<T>(a, it);
     while (it < total) {
         // look ahead: the next ticket and its row bounds are in flight while this item is processed
         const unsigned long long nit = take_ticket();
         CsrItem nxt;
-        if (nit < total) nxt = csr_load_item<T, G>(a, nit);
-        if (!cur.skip) csr_process_item<T, E, G, UNROLL, R, D>(a, cur);
+        if (nit < total) nxt = csr_load_item<T>(a, nit);
+        for (int j = 0; j < cur.count; ++j) {
+            const int start = __shfl_sync(FULL, cur.rp, j);
+            const int end = __shfl_sync(FULL, cur.rp, j + 1);
+            // rows longer than seg_len are covered by their segments + fix-up
+            if (cur.to_partial || end - start <= a.seg_len)
+                csr_process_range<T, E, G, UNROLL, R, D>(a, start, end, cur.chunk, cur.first + j, cur.to_partial);
+        }
         it = nit;
         cur = nxt;
     }

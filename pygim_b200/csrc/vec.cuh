@@ -85,6 +85,19 @@ __device__ __forceinline__ void fma_pack(typename Arith<T>::Acc (&acc)[E], const
     }
 }
 
+// INT8, 16 elements per 16-byte word: one IDP.4A per element and no unpacking.  The multiplier byte is
+// placed in lane j of the second operand (zeros elsewhere), so dp4a(word, v << 8j, acc) = acc + word.byte[j] * v
+// with both bytes taken as signed - exactly the sign-extended multiply-add, modulo 2^32.
+template <>
+__device__ __forceinline__ void fma_pack<int8_t, 16>(uint32_t (&acc)[16], const Pack<int8_t, 16> &b, int v) {
+    union { Pack<int8_t, 16> p; int w[4]; } u;
+    u.p = b;
+    const int vb = v & 0xff;
+    const int sel[4] = {vb, vb << 8, vb << 16, vb << 24};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = (uint32_t)__dp4a(u.w[k >> 2], sel[k & 3], (int)acc[k]);
+}
+
 template <typename T, int E>
 __device__ __forceinline__ Pack<T, E> narrow(const typename Arith<T>::Acc (&acc)[E]) {
     Pack<T, E> r;

@@ -53,17 +53,27 @@ def all_gather_rows(out: torch.Tensor, row_counts: Sequence[int], mine: torch.Te
             dist.broadcast(chunk, src=ranks[i], group=group)
 
 
+def _gather_views(views: Sequence[torch.Tensor], group=None) -> None:
+    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+    for i, v in enumerate(views):
+        if v.numel():
+            dist.broadcast(v, src=ranks[i], group=group)
+
+
 class ShardedSpMM:
     """C = A @ B with A row-sharded over the ranks of `group`.
 
     `adj` is the FULL adjacency (every rank passes the same one; only the local row range is planned)
     unless `splits` and `local_adj` are given.  `make_local` builds the per-rank operator from the local
     shard - by default the CUDA plan of backend_pim.spmm; tests on CPU inject a checker there.
+
+    `chunks` > 1 cuts the local row range into that many nnz-balanced sub-blocks, each with its own plan:
+    the all-gather of sub-block k (NCCL's stream) then overlaps the SpMM of sub-block k+1 (compute stream).
     """
 
     def __init__(self, adj: Optional[SparseTensor], args, group=None, splits: Optional[Sequence[int]] = None,
                  local_adj: Optional[SparseTensor] = None,
-                 make_local: Optional[Callable[[SparseTensor, object], object]] = None):
+                 make_local: Optional[Callable[[SparseTensor, object], object]] = None, chunks: int = 1):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -82,8 +92,24 @@ class ShardedSpMM:
         if make_local is None:
             from .backend_pim.spmm import prepare_pim_spmm
             make_local = prepare_pim_spmm
-        local_args = types.SimpleNamespace(**vars(args))
-        self.local = make_local(local_adj, local_args)
+        self.chunks = max(1, int(chunks)) if self.world > 1 else 1
+        if self.chunks == 1:
+            self.sub = [0, self.r1 - self.r0]
+            self.locals = [make_local(local_adj, types.SimpleNamespace(**vars(args)))]
+            self.all_sub = None
+        else:
+            self.sub = row_splits_by_nnz(local_adj.csr()[0], self.chunks)      # local row offsets of the sub-blocks
+            self.locals = [make_local(shard_rows(local_adj, self.sub[k], self.sub[k + 1]),
+                                      types.SimpleNamespace(**vars(args))) for k in range(self.chunks)]
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, self.sub, group=group)            # every rank's sub-block offsets
+            self.all_sub = gathered
+        self.local = self.locals[0]
+
+    def _sub_block_views(self, out: torch.Tensor, k: int):
+        """Rows of sub-block k of every rank, as views of the full result."""
+        return [out[self.splits[i] + self.all_sub[i][k]: self.splits[i] + self.all_sub[i][k + 1]]
+                for i in range(self.world)]
 
     def mul(self, B: torch.Tensor, out: Optional[torch.Tensor] = None, gather: bool = True) -> torch.Tensor:
         """Returns the full [N x H] result (on B's device) when `gather`, else a view of the local block."""
@@ -91,9 +117,24 @@ class ShardedSpMM:
         if out is None:
             out = torch.empty((self.nrows, self.hidden_size), dtype=B.dtype, device=B.device)
         mine = out[self.r0:self.r1]
-        self.local.mul(B, out=mine)
-        if gather and self.world > 1:
-            all_gather_rows(out, self.row_counts, mine, self.group)
+        if self.chunks == 1:
+            self.locals[0].mul(B, out=mine)
+            if gather and self.world > 1:
+                all_gather_rows(out, self.row_counts, mine, self.group)
+            return out if gather else mine
+        pending = []
+        for k in range(self.chunks):
+            block = mine[self.sub[k]:self.sub[k + 1]]
+            self.locals[k].mul(B, out=block)
+            if gather:
+                # async: NCCL waits for the kernel just enqueued, then runs beside the next sub-block's SpMM
+                views = self._sub_block_views(out, k)
+                if dist.get_backend(self.group) == "nccl":
+                    pending.append(dist.all_gather(views, block, group=self.group, async_op=True))
+                else:   # equal-size-only backends (gloo in the CPU tests): one broadcast per block
+                    _gather_views(views, self.group)
+        for w in pending:
+            w.wait()
         return out if gather else mine
 
     def mul_gather_only(self, out: torch.Tensor) -> torch.Tensor:
@@ -103,5 +144,6 @@ class ShardedSpMM:
         return out
 
     def free(self):
-        if hasattr(self.local, "free"):
-            self.local.free()
+        for op in self.locals:
+            if hasattr(op, "free"):
+                op.free()

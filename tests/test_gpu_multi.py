@@ -28,12 +28,14 @@ def _worker(rank, world, port, ret):
         for dtype, hidden in ((torch.float32, 64), (torch.int32, 32)):
             x = graphgen.reference_features(n, hidden, dtype, seed=1)
             args = types.SimpleNamespace(data_type=dtype, sp_format="CSR", hidden_size=hidden, sp_parts=1, ds_parts=1)
-            op = ShardedSpMM(adj.to("cuda"), args)
-            out = op.mul(x.cuda())
-            torch.cuda.synchronize()
             want = O.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy())
-            ok = ok and bool(np.array_equal(out.cpu().numpy(), want))
-            op.free()
+            for chunks in (1, 3):
+                op = ShardedSpMM(adj.to("cuda"), args, chunks=chunks)
+                for _ in range(2):
+                    out = op.mul(x.cuda())
+                torch.cuda.synchronize()
+                ok = ok and bool(np.array_equal(out.cpu().numpy(), want))
+                op.free()
         ret[rank] = ok
         pim_ops.dpu_release()
     finally:

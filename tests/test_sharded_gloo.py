@@ -38,9 +38,11 @@ def _worker(rank, world, port, ret):
         args = types.SimpleNamespace(data_type=torch.float32, sp_format="CSR", hidden_size=16, sp_parts=1, ds_parts=1)
         op = ShardedSpMM(adj, args, make_local=_OracleLocal)
         out = op.mul(x)
+        op2 = ShardedSpMM(adj, args, make_local=_OracleLocal, chunks=3)       # overlapped sub-block schedule
+        out2 = op2.mul(x)
         full = _OracleLocal(adj, args).mul(x, out=torch.empty(n, 16))
         nnz_local = int(op.local_adj.nnz())
-        ret[rank] = (bool(torch.equal(out, full)), op.splits, nnz_local, adj.nnz())
+        ret[rank] = (bool(torch.equal(out, full)) and bool(torch.equal(out2, full)), op.splits, nnz_local, adj.nnz())
     finally:
         dist.destroy_process_group()
 
