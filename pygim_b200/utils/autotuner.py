@@ -1,13 +1,106 @@
-"""Retargeted autotuner (utils/autotuner.py of the reference): picks the (sp_parts, ds_parts) split and
-kernel parameters from graph statistics instead of UPMEM bandwidth tables.  [first cut: column tiling]"""
+"""Retargeted autotuner: picks the (sp_parts, ds_parts) split and the kernel scheduling parameters from graph
+statistics and a small B200 cost model.
+
+The reference's `autotune(datadir, dataset, hidden_size, split_set, blnc_set)` (utils/autotuner.py:263-343)
+scores `load/HOST_DPU_BW + merge + max_nnz_per_dpu/FMA_THROUGHPUT + retrieve/DPU_HOST_BW` with UPMEM
+micro-benchmark tables (:23-89) over `sp_ds_set = [(1,32),(2,16)]` x balance and returns
+`[sp_parts, ds_parts, balance, balance_tsklt, None]`.  Here the same shape of answer comes from:
+
+* graph statistics (rows, nnz, mean / max / CV of the row degree) - `GraphStats`;
+* measured B200 constants (`DeviceModel`): HBM copy bandwidth, the L2->SM gather rate as a function of the
+  gathered row's bytes, the HBM random-row efficiency when B does not fit L2, the L2-resident capacity;
+* an analytic time per (sp_parts, ds_parts): every dense tile re-streams A from HBM and gathers nnz rows of
+  `w*s` bytes either out of L2 (tile resident) or out of HBM; sparse parts >= 1 add a read-modify-write of C.
+
+`choose_ds_parts` is the closed-form special case used by the front-ends when the caller passes ds_parts=0.
+"""
 from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from .space import For, Space, Table
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+@dataclass
+class DeviceModel:
+    """B200 constants, measured with bench.py / ncu in round 1 (profiles/r01_*.json)."""
+    hbm_gbs: float = 6541.0
+    l2_bytes: int = 126 * 2 ** 20
+    l2_resident_fraction: float = 0.46          # read-shared data is held in both die-local L2 halves
+    sm_count: int = 148
+    launch_us: float = 4.0
+    # a row is a dependent chain (index load -> gather -> shuffle tree -> store) that one warp walks alone:
+    # short-row graphs are bound by rows x row_latency / resident warps (measured on products-shape, 16-byte rows)
+    row_latency_us: float = 1.9
+    resident_warps_per_sm: int = 24
+    # gather rate out of L2 (TB/s of gathered payload) vs bytes per gathered row
+    l2_gather_tbs: Dict[int, float] = field(default_factory=lambda: {16: 3.0, 32: 6.0, 64: 12.0, 128: 16.0,
+                                                                     256: 18.5, 512: 18.0})
+    # fraction of hbm_gbs reached when the rows are gathered from HBM (B >> L2)
+    hbm_gather_eff: Dict[int, float] = field(default_factory=lambda: {16: 0.08, 32: 0.15, 64: 0.35, 128: 0.61,
+                                                                      256: 0.81, 512: 0.93})
+
+    @classmethod
+    def from_environment(cls, info: Optional[dict] = None) -> "DeviceModel":
+        m = cls()
+        path = os.path.join(_ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(path):
+            try:
+                with open(path) as f:
+                    m.hbm_gbs = float(json.load(f)["hbm_gbs"])
+            except Exception:
+                pass
+        if info:
+            m.l2_bytes = int(info.get("l2_bytes", m.l2_bytes))
+            m.sm_count = int(info.get("sm_count", m.sm_count))
+        return m
+
+    @staticmethod
+    def _interp(table: Dict[int, float], row_bytes: float) -> float:
+        keys = sorted(table)
+        if row_bytes <= keys[0]:
+            return table[keys[0]] * row_bytes / keys[0]
+        if row_bytes >= keys[-1]:
+            return table[keys[-1]]
+        for lo, hi in zip(keys, keys[1:]):
+            if lo <= row_bytes <= hi:
+                t = (math.log2(row_bytes) - math.log2(lo)) / (math.log2(hi) - math.log2(lo))
+                return table[lo] + t * (table[hi] - table[lo])
+        return table[keys[-1]]
+
+
+@dataclass
+class GraphStats:
+    nrows: int
+    ncols: int
+    nnz: int
+    mean_degree: float
+    max_degree: int
+    cv_degree: float          # coefficient of variation (degree skew)
+    empty_rows: int
+
+    @classmethod
+    def from_rowptr(cls, rowptr, ncols: Optional[int] = None) -> "GraphStats":
+        import torch
+        rp = rowptr.to(torch.int64).cpu()
+        deg = (rp[1:] - rp[:-1]).to(torch.float64)
+        n = int(deg.numel())
+        mean = float(deg.mean()) if n else 0.0
+        std = float(deg.std(unbiased=False)) if n else 0.0
+        return cls(n, int(ncols if ncols is not None else n), int(rp[-1]) if n else 0, mean,
+                   int(deg.max()) if n else 0, std / mean if mean > 0 else 0.0, int((deg == 0).sum()))
 
 
 def choose_ds_parts(n_cols: int, hidden: int, elem_size: int, l2_bytes: int, l2_fraction: float = 0.46) -> int:
-    """Smallest number (1, 2 or 4) of equal column tiles for which one B tile (n_cols x hidden/ds x elem_size) fits in
-    `l2_fraction` of L2.  B200's L2 is two die-local halves and read-shared data ends up in both, so the
-    budget for the resident tile is well below the nominal 126 MB; the streaming A/C traffic needs room too.
-    Tiles keep 16-byte rows (hidden/ds * elem_size % 16 == 0) so the vector kernels stay usable."""
+    """Smallest number (1, 2 or 4) of equal column tiles for which one B tile (n_cols x hidden/ds x elem_size)
+    fits in `l2_fraction` of L2.  B200's L2 is two die-local halves and read-shared data ends up in both, so the
+    budget for the resident tile is well below the nominal 126 MB; the streaming A/C traffic needs room too."""
     budget = l2_bytes * l2_fraction
     for ds in (1, 2, 4):
         if hidden % ds:
@@ -20,3 +113,69 @@ def choose_ds_parts(n_cols: int, hidden: int, elem_size: int, l2_bytes: int, l2_
     # B is far larger than L2 (ogbn-products-shape): the gather is served by HBM whatever the tiling, and every
     # extra tile re-streams A and shortens the gathered rows (measured: 5.6 ms at ds=1, 12 ms at ds=2).
     return 1
+
+
+def predict_ms(stats: GraphStats, hidden: int, elem_size: int, sp_parts: int, ds_parts: int,
+               dev: Optional[DeviceModel] = None, fmt: str = "CSR") -> float:
+    """Analytic time of one SpMM under the (sp_parts, ds_parts) tiling."""
+    dev = dev or DeviceModel()
+    w = -(-hidden // ds_parts)                              # ceil: widest dense tile
+    row_bytes = w * elem_size
+    idx_bytes = (4 if fmt == "CSR" else 8) + elem_size      # per nonzero: (rowind) + colind + value
+    cols_per_part = -(-stats.ncols // sp_parts)
+    tile_bytes = cols_per_part * row_bytes
+    resident = tile_bytes <= dev.l2_bytes * dev.l2_resident_fraction
+    total_us = 0.0
+    for sp in range(sp_parts):
+        nnz = stats.nnz / sp_parts
+        for _ in range(ds_parts):
+            stream_us = (nnz * idx_bytes + 4 * stats.nrows + tile_bytes * (1 if resident else 0)
+                         + stats.nrows * row_bytes * (1 if sp == 0 else 3)) / (dev.hbm_gbs * 1e3)
+            if resident:
+                gather_us = nnz * row_bytes / (DeviceModel._interp(dev.l2_gather_tbs, row_bytes) * 1e6)
+            else:
+                gather_us = nnz * row_bytes / (dev.hbm_gbs * 1e3 * DeviceModel._interp(dev.hbm_gather_eff, row_bytes))
+                stream_us += gather_us                       # the gather itself is HBM traffic
+                gather_us = 0.0
+            chain_us = stats.nrows * dev.row_latency_us / (dev.sm_count * dev.resident_warps_per_sm)
+            total_us += max(stream_us, gather_us, chain_us) + dev.launch_us
+    return total_us / 1e3
+
+
+def default_space(hidden: int) -> Space:
+    """(sp_parts, ds_parts) candidates: the reference's pairs rescaled to what a GPU needs (utils/autotuner.py:259-263
+    uses [(1,32),(2,16)] because one UPMEM rank holds one B slice)."""
+    return For("sp_parts", [1, 2, 4]) * For("ds_parts", [d for d in (1, 2, 4, 8) if hidden % d == 0])
+
+
+def autotune(adj_or_stats, hidden_size: int, split_set: Optional[Sequence[Tuple[int, int]]] = None,
+             blnc_set: Sequence[int] = (0, 2), elem_size: int = 4, fmt: str = "CSR",
+             dev: Optional[DeviceModel] = None) -> List:
+    """Returns `[sp_parts, ds_parts, balance, balance_tsklt, extra]` like the reference (utils/autotuner.py:338).
+
+    `adj_or_stats`: a SparseTensor-like object (`.csr()`, `.size(1)`) or a GraphStats.  `split_set`: explicit
+    (sp, ds) pairs (the reference's argument) or None for `default_space`.  On the GPU both balancing levels are
+    nnz-based (long rows are cut into segments, work is ticketed), so `balance`/`balance_tsklt` are "nnz" unless
+    the graph has no skew at all, where plain row tickets ("row") suffice.  `extra` carries the scheduling
+    parameters and the predicted time."""
+    if isinstance(adj_or_stats, GraphStats):
+        stats = adj_or_stats
+    else:
+        stats = GraphStats.from_rowptr(adj_or_stats.csr()[0], adj_or_stats.size(1))
+    dev = dev or DeviceModel.from_environment()
+    space: Space = Table(["sp_parts", "ds_parts"], split_set) if split_set else default_space(hidden_size)
+    best, best_ms = None, float("inf")
+    for cfg in space.iter_dict():
+        ms = predict_ms(stats, hidden_size, elem_size, cfg["sp_parts"], cfg["ds_parts"], dev, fmt)
+        if ms < best_ms:
+            best, best_ms = cfg, ms
+    slots = dev.sm_count * 64
+    seg_len = 256
+    while seg_len < stats.nnz / max(1, slots * 8) and seg_len < 4096:
+        seg_len *= 2
+    skewed = stats.max_degree > seg_len or stats.cv_degree > 0.5
+    balance = "nnz" if skewed else "row"
+    extra = {"predicted_ms": best_ms, "seg_len": seg_len,
+             "rows_per_ticket": int(max(1, min(31, 256 // max(1.0, stats.mean_degree)))),
+             "kernel": "coo-segmented" if fmt == "COO" else "csr-ticketed"}
+    return [best["sp_parts"], best["ds_parts"], balance, "nnz", extra]
