@@ -243,17 +243,23 @@ def run_ours(a):
         ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj,
                               make_local=lambda _adj, _args, _h=h: plans[_h]) for h in sweep}
     else:
-        ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj, chunks=a.chunks) for h in sweep}
+        ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj, chunks=a.chunks,
+                              fused=(a.gather == "fused"), use_multicast=not a.no_multicast) for h in sweep}
         plans = {h: ops[h].locals[0] for h in sweep}
     x_dev = {h: graphgen.reference_features(n, h, dtype, seed=h, device=str(dev)) for h in sweep}
     # full outputs (every rank ends with all rows, ready for the next layer)
     c_full = {h: torch.empty((n, h), dtype=dtype, device=dev) for h in sweep}
 
+    c_last = dict(c_full)
+
     def step_device(record=None):
         for i, h in enumerate(sweep):
             if record is not None:
                 record[i][0].record()
-            ops[h].mul(x_dev[h], out=c_full[h])        # N > 1: SpMM of the row block(s) + all-gather
+            if world > 1 and a.gather == "fused":
+                c_last[h] = ops[h].mul(x_dev[h])       # rows land in every peer's symmetric buffer (no collective)
+            else:
+                ops[h].mul(x_dev[h], out=c_full[h])    # N > 1: SpMM of the row block(s) + NCCL all-gather
             if record is not None:
                 record[i][1].record()
 
@@ -335,7 +341,7 @@ def run_ours(a):
         parity = True
         for h in sweep:
             want = O.spmm_csr_rowpar(rp_h, cl_h, None, x_host[h].numpy(), nthreads=O.max_threads())
-            parity = parity and bool(np.array_equal(want, c_full[h][r0:r0 + rows_chk].cpu().numpy())) \
+            parity = parity and bool(np.array_equal(want, c_last[h][r0:r0 + rows_chk].cpu().numpy())) \
                 and bool(np.array_equal(want, c_host[h][:rows_chk].numpy()))
 
     if rank != 0:
@@ -395,8 +401,9 @@ def run_ours(a):
                                                                          "/".join(map(str, sweep))),
                    "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": a.format, "sp_parts": 1,
                    "ds_parts": {str(h): ds_parts[h] for h in sweep},
-                   "sharding": "rows by nnz over %d GPUs, B replicated, %d sub-blocks per rank, NCCL all-gather of C "
-                               "inside the timing (overlapped with the next sub-block's SpMM)" % (world, a.chunks)
+                   "sharding": ("rows by nnz over %d GPUs, B replicated, all-gather of C %s, inside the timing"
+                                % (world, "fused into the kernel epilogue (NVLink peer stores)" if a.gather == "fused"
+                                   else "by NCCL (%d sub-blocks per rank)" % a.chunks))
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (A = %.0f MB streams through a %.0f MB L2 every launch)"
                          % ((8.0 * nnz) / 1e6, info["l2_bytes"] / 1e6)},
@@ -428,6 +435,9 @@ def main():
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: one untimed-quality e2e pass only")
     ap.add_argument("--ds-parts", type=int, default=0, help="dense column parts per launch group; 0 = automatic")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: all-gather fused into the kernel epilogue (peer stores) or a separate NCCL collective")
+    ap.add_argument("--no-multicast", action="store_true", help="fused gather: per-peer stores instead of multimem.st")
     ap.add_argument("--chunks", type=int, default=1, help="N > 1: sub-blocks per rank (all-gather/compute overlap)")
     a = ap.parse_args()
     if a.impl == "reference":

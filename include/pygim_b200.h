@@ -137,6 +137,16 @@ PYGIM_API int pygim_spmm_run_group_device(pygim_handle_t handle, int n_ds, const
  * dense_split copies): the dense column parts become column tiles of B/C. */
 PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ldb, void *C, int64_t ldc, void *stream);
 
+/* Row-sharded multi-GPU run with the all-gather FUSED into the kernel epilogue (no reference counterpart: the
+ * reference gathers DPU row blocks with dpu_push_xfer(FROM_DPU) and merges them on the host,
+ * spmm_default/spmm_mul_csr.c:385-410,479-554).  This rank's plan covers rows [row_offset, row_offset + nrows)
+ * of the global result; every output row is stored to that row of EACH of the n_peers (<= 8) result matrices
+ * C_peers[q] - NVLink peer mappings of the other ranks' buffers, the local buffer included - or, when
+ * C_multicast is not NULL, once to an NVSwitch multicast mapping of them (multimem.st).  CSR, sp_parts == 1.
+ * The caller provides the cross-rank barriers before (peers done reading) and after (rows visible) the call. */
+PYGIM_API int pygim_spmm_device_peers(pygim_handle_t handle, const void *B, int64_t ldb, void *const *C_peers,
+                                      int n_peers, void *C_multicast, int64_t ldc, int64_t row_offset, void *stream);
+
 /* The five phase timers the reference prints as [DATA]load_sparse_time / load_dense_time /
  * kernel_time / retrieve_result_time / alignment_time (spmm_mul_csr.c:563-580), in ms, for the
  * last pygim_spmm_run_group_host call on this handle (alignment is always 0: the kernels write C

@@ -21,7 +21,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 SYMBOLS = [
     "pygim_last_error", "pygim_abi_version", "pygim_dpu_init_ranks", "pygim_dpu_init_dpus", "pygim_dpu_release",
     "pygim_device_info", "pygim_spmm_to_device_group", "pygim_spmm_free_group", "pygim_plan_set_option",
-    "pygim_plan_stats", "pygim_spmm_run_group_host", "pygim_spmm_run_group_device", "pygim_spmm_device",
+    "pygim_plan_stats", "pygim_spmm_run_group_host", "pygim_spmm_run_group_device", "pygim_spmm_device", "pygim_spmm_device_peers",
     "pygim_last_timers", "pygim_last_launches", "pygim_partition_rows_by_nnz", "pygim_partition_rows_even",
 ]
 
@@ -51,6 +51,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pygim_spmm_run_group_host.argtypes = [C.c_uint64, ci, P(vp), P(i64), vp, i64]
     lib.pygim_spmm_run_group_device.argtypes = [C.c_uint64, ci, P(vp), P(i64), vp, i64, vp]
     lib.pygim_spmm_device.argtypes = [C.c_uint64, vp, i64, vp, i64, vp]
+    lib.pygim_spmm_device_peers.argtypes = [C.c_uint64, vp, i64, P(vp), ci, vp, i64, i64, vp]
     lib.pygim_last_timers.argtypes = [C.c_uint64, P(C.c_double)]
     lib.pygim_last_launches.argtypes = [C.c_uint64, P(i64)]
     lib.pygim_partition_rows_by_nnz.argtypes = [vp, i64, ci, P(i64)]

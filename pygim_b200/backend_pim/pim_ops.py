@@ -287,6 +287,29 @@ def spmm_run_dense(handle: int, B: torch.Tensor, out: Optional[torch.Tensor] = N
     return out
 
 
+def spmm_run_dense_peers(handle: int, B: torch.Tensor, peer_ptrs: Sequence[int], multicast_ptr: int, ldc: int,
+                         row_offset: int) -> None:
+    """Row-sharded multi-GPU run with the all-gather fused into the kernel epilogue
+    (pygim_spmm_device_peers): this rank's rows are stored at `row_offset` of every peer's result matrix
+    (`peer_ptrs`: NVLink-mapped base pointers, own buffer included; `multicast_ptr`: NVSwitch multicast
+    mapping or 0).  Asynchronous on the current stream; the caller owns the cross-rank barriers."""
+    m = _meta(handle)
+    if not B.is_cuda:
+        raise _lib.PygimError("the fused all-gather path needs a CUDA operand")
+    if B.dtype != m.dtype or B.dim() != 2 or B.size(1) != m.h_size or B.size(0) != m.total_cols:
+        raise _lib.PygimError("dense operand has shape %s/%s, expected (%d, %d) %s"
+                              % (tuple(B.shape), B.dtype, m.total_cols, m.h_size, m.dtype))
+    if B.stride(1) != 1 and B.numel():
+        B = B.contiguous()
+    ldb = B.stride(0) if B.size(0) > 1 else max(B.size(1), 1)
+    ptrs = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(B.device):
+        stream = torch.cuda.current_stream(B.device).cuda_stream
+        _lib.check(_lib.lib().pygim_spmm_device_peers(int(handle), B.data_ptr(), ldb, ptrs, len(peer_ptrs),
+                                                      C.c_void_p(int(multicast_ptr) or None), int(ldc),
+                                                      int(row_offset), C.c_void_p(stream)))
+
+
 def _grande_reassemble(m: _GroupMeta, B_parts: Sequence[torch.Tensor]) -> torch.Tensor:
     """Undo grande.dense_split (grande.py:12-23): for sparse part i the next len(cols_i) entries are
     its row block's column slices, each `pad` columns wide (the tail beyond the slice's real width is

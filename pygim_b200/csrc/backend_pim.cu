@@ -238,8 +238,14 @@ template <typename L> static cudaError_t dispatch_coo(int dtype, const L &l, int
 }
 
 // C[:, col0:col0+w] (+)= A_i * B_tile[rows_i, :]  for one (sparse part, dense tile)
+struct PeerDst {        // destinations of the fused all-gather (empty => plain local C)
+    int n = 0;
+    char *ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    char *mc = nullptr;
+};
+
 static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char *C, long long ldc, long long width,
-                    bool accumulate, cudaStream_t stream) {
+                    bool accumulate, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0) {
     const size_t s = dtype_size(g->dtype);
     cudaError_t err;
     if (g->format == PYGIM_CSR) {
@@ -277,6 +283,9 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.ldc = ldc;
         l.ldp = ldp;
         l.accumulate = accumulate ? 1 : 0;
+        l.n_peers = peers ? peers->n : 0;
+        l.mc = (peers && peers->mc) ? peers->mc + peer_off : nullptr;
+        for (int q = 0; q < 8; ++q) l.peers[q] = (peers && q < peers->n) ? peers->ptr[q] + peer_off : nullptr;
         l.sm_count = g_ctx.sm_count;
         l.ticket = g->d_ticket;
         l.ticket_base = &g->ticket_base;
@@ -310,7 +319,7 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
 // The (sparse part x dense part) loop of spmm_pim_csr / spmm_host_*_group (ops.hpp:42-62):
 // dense part j of width h_j lands at column offset sum_{k<j} h_k; sparse part 0 overwrites, parts >= 1 add.
 static int run_group_device(Group *g, int n_ds, const void *const *B_parts, const long long *ldb, void *C,
-                            long long ldc, cudaStream_t stream) {
+                            long long ldc, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0) {
     if (n_ds != (int)g->dense_cols.size())
         return fail(PYGIM_ERR_INVALID, "expected %d dense parts, got %d", (int)g->dense_cols.size(), n_ds);
     const size_t s = dtype_size(g->dtype);
@@ -322,7 +331,7 @@ static int run_group_device(Group *g, int n_ds, const void *const *B_parts, cons
             const long long w = g->dense_cols[j];
             const char *B = static_cast<const char *>(B_parts[j]) + (size_t)brow * (size_t)ldb[j] * s;
             char *Ct = static_cast<char *>(C) + (size_t)ccol * s;
-            int rc = run_tile(g, g->parts[i], B, ldb[j], Ct, ldc, w, i > 0, stream);
+            int rc = run_tile(g, g->parts[i], B, ldb[j], Ct, ldc, w, i > 0, stream, peers, peer_off + (size_t)ccol * s);
             if (rc) return rc;
             ccol += w;
         }
@@ -552,6 +561,35 @@ PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ld
         col += g->dense_cols[j];
     }
     return run_group_device(g, (int)parts.size(), parts.data(), lds.data(), C, ldc, static_cast<cudaStream_t>(stream));
+}
+
+PYGIM_API int pygim_spmm_device_peers(pygim_handle_t handle, const void *B, int64_t ldb, void *const *C_peers,
+                                      int n_peers, void *C_multicast, int64_t ldc, int64_t row_offset, void *stream) {
+    Group *g = as_group(handle);
+    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    if (!B || !C_peers) return fail(PYGIM_ERR_INVALID, "null buffer");
+    if (n_peers < 1 || n_peers > 8) return fail(PYGIM_ERR_INVALID, "n_peers must be 1..8, got %d", n_peers);
+    if (g->format != PYGIM_CSR) return fail(PYGIM_ERR_INVALID, "the fused all-gather epilogue is CSR-only");
+    if (g->parts.size() != 1)   // partial products of sparse parts >= 1 would need a remote read-modify-write
+        return fail(PYGIM_ERR_INVALID, "the fused all-gather epilogue needs sp_parts == 1");
+    const size_t s = dtype_size(g->dtype);
+    PeerDst dst;
+    dst.n = n_peers;
+    const size_t row_bytes = (size_t)row_offset * (size_t)ldc * s;
+    for (int q = 0; q < n_peers; ++q) {
+        if (!C_peers[q]) return fail(PYGIM_ERR_INVALID, "peer %d has a null buffer", q);
+        dst.ptr[q] = static_cast<char *>(C_peers[q]) + row_bytes;
+    }
+    dst.mc = C_multicast ? static_cast<char *>(C_multicast) + row_bytes : nullptr;
+    std::vector<const void *> parts(g->dense_cols.size());
+    std::vector<long long> lds(g->dense_cols.size(), ldb);
+    long long col = 0;
+    for (size_t j = 0; j < g->dense_cols.size(); ++j) {
+        parts[j] = static_cast<const char *>(B) + (size_t)col * s;
+        col += g->dense_cols[j];
+    }
+    return run_group_device(g, (int)parts.size(), parts.data(), lds.data(), dst.ptr[0], ldc,
+                            static_cast<cudaStream_t>(stream), &dst, 0);
 }
 
 PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,

@@ -105,6 +105,9 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.ldc = l.ldc;
     a.ldp = l.ldp;
     a.accumulate = l.accumulate;
+    a.n_peers = l.n_peers;
+    a.mc = static_cast<T *>(l.mc);
+    for (int p = 0; p < kMaxPeers; ++p) a.peers[p] = p < l.n_peers ? static_cast<T *>(l.peers[p]) : nullptr;
     const long long items = (long long)l.n_seg + l.nrows;
     if (items == 0 || a.nvec == 0) return cudaSuccess;
     cudaError_t err;
@@ -127,6 +130,8 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
         f.ldc = l.ldc;
         f.ncols = (int)l.ncols;
         f.accumulate = l.accumulate;
+        f.n_peers = l.n_peers;      // the fix-up uses the unicast mappings (scalar stores)
+        for (int p = 0; p < kMaxPeers; ++p) f.peers[p] = a.peers[p];
         const int threads = l.ncols >= 128 ? 128 : (l.ncols > 32 ? 64 : 32);
         csr_fixup_kernel<T><<<l.n_long, threads, 0, l.stream>>>(f);
         ++*launches;

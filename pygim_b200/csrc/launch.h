@@ -23,6 +23,11 @@ struct CsrLaunch {
     long long ncols;          // dense columns of this tile
     long long ldb, ldc, ldp;  // row strides in elements
     int accumulate;
+    // fused all-gather: n_peers > 0 => rows go to peers[p] + (same offset as C) for every p (C is then unused);
+    // mc != NULL => an NVSwitch multicast mapping of the same buffers (one multimem.st instead of n_peers stores)
+    void *peers[8];
+    void *mc;
+    int n_peers;
     int sm_count;
     unsigned long long *ticket;        // device work counter of the plan (monotonic)
     unsigned long long *ticket_base;   // host mirror: value of *ticket when the next launch starts

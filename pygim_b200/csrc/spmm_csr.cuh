@@ -26,6 +26,8 @@
 
 namespace pygim {
 
+constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
+
 struct Seg {       // one nnz-bounded piece of a long row
     int row;
     int start;     // first nonzero (index into colind/val)
@@ -52,9 +54,31 @@ template <typename T> struct CsrArgs {
     int col_chunks;    // ceil(nvec / G): every item is processed once per chunk of G words
     long long ldb, ldc, ldp;
     int accumulate;    // 0: C = A*B, 1: C += A*B
+    // fused all-gather (row-sharded multi-GPU): when n_peers > 0 every output row is stored to the same
+    // offset of every peer's C (NVLink-mapped pointers, the local one included) instead of a.C; when mc is
+    // set it is an NVSwitch multicast mapping of those buffers and ONE multimem.st reaches every GPU.
+    T *peers[kMaxPeers];
+    T *mc;
+    int n_peers;
 };
 
 constexpr int kCsrThreads = 256;
+
+// store one word of an output row to every destination of the fused all-gather
+template <typename T, int E>
+__device__ __forceinline__ void st_peers(T *const *peers, int n_peers, T *mc, long long off, const Pack<T, E> &v) {
+    if constexpr (sizeof(T) * E == 16) {
+        if (mc != nullptr) {
+            union { Pack<T, E> p; float4 f; } u;
+            u.p = v;
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + off),
+                         "f"(u.f.x), "f"(u.f.y), "f"(u.f.z), "f"(u.f.w)
+                         : "memory");
+            return;
+        }
+    }
+    for (int p = 0; p < n_peers; ++p) st_plain<T, E>(peers[p] + off, v);
+}
 
 struct CsrItem {
     int first;         // segment: slot of the partial buffer; rows: first row of the ticket
@@ -187,6 +211,9 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
     if (sub == 0 && active) {
         if (to_partial) {
             st_plain<T, E>(a.partial + (long long)dst_row * a.ldp + (long long)vec * E, narrow<T, E>(acc));
+        } else if (a.n_peers > 0) {
+            st_peers<T, E>(a.peers, a.n_peers, a.mc, (long long)dst_row * a.ldc + (long long)vec * E,
+                           narrow<T, E>(acc));
         } else {
             T *p = a.C + (long long)dst_row * a.ldc + (long long)vec * E;
             if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(p));
@@ -239,6 +266,8 @@ template <typename T> struct FixupArgs {
     long long ldp, ldc;
     int ncols;
     int accumulate;
+    T *peers[kMaxPeers];
+    int n_peers;
 };
 
 template <typename T> __global__ void csr_fixup_kernel(const FixupArgs<T> a) {
@@ -252,6 +281,10 @@ template <typename T> __global__ void csr_fixup_kernel(const FixupArgs<T> a) {
             Pack<T, 1> p;
             p.e[0] = a.partial[(long long)s * a.ldp + c];
             add_old<T, 1>(acc, p);
+        }
+        if (a.n_peers > 0) {
+            for (int p = 0; p < a.n_peers; ++p) a.peers[p][(long long)row * a.ldc + c] = (T)acc[0];
+            continue;
         }
         T *dst = a.C + (long long)row * a.ldc + c;
         if (a.accumulate) {

@@ -69,11 +69,17 @@ class ShardedSpMM:
 
     `chunks` > 1 cuts the local row range into that many nnz-balanced sub-blocks, each with its own plan:
     the all-gather of sub-block k (NCCL's stream) then overlaps the SpMM of sub-block k+1 (compute stream).
+
+    `fused=True` (CUDA, CSR, sp_parts == 1) removes the collective altogether: the result lives in a
+    symmetric-memory buffer and the SpMM kernel's epilogue stores every output row straight into every
+    peer's copy over NVLink (one multimem.st through the NVSwitch when multicast is available, else one store
+    per peer), bracketed by two device-side barriers.  The transfer overlaps the gathers row by row.
     """
 
     def __init__(self, adj: Optional[SparseTensor], args, group=None, splits: Optional[Sequence[int]] = None,
                  local_adj: Optional[SparseTensor] = None,
-                 make_local: Optional[Callable[[SparseTensor, object], object]] = None, chunks: int = 1):
+                 make_local: Optional[Callable[[SparseTensor, object], object]] = None, chunks: int = 1,
+                 fused: bool = False, use_multicast: bool = True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -105,6 +111,31 @@ class ShardedSpMM:
             dist.all_gather_object(gathered, self.sub, group=group)            # every rank's sub-block offsets
             self.all_sub = gathered
         self.local = self.locals[0]
+        self.fused = bool(fused) and self.world > 1
+        self.use_multicast = use_multicast
+        self._symm = {}          # dtype -> (buffer, handle)
+        if self.fused and self.chunks != 1:
+            raise ValueError("fused=True replaces the chunked NCCL schedule; use chunks=1")
+
+    # -- fused all-gather: symmetric result buffer + peer stores from the kernel epilogue
+    def _symmetric_out(self, dtype: torch.dtype, device: torch.device):
+        if dtype not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty((self.nrows, self.hidden_size), dtype=dtype, device=device)
+            hdl = symm_mem.rendezvous(buf, group.group_name)
+            self._symm[dtype] = (buf, hdl)
+        return self._symm[dtype]
+
+    def _mul_fused(self, B: torch.Tensor) -> torch.Tensor:
+        from .backend_pim import pim_ops
+        buf, hdl = self._symmetric_out(B.dtype, B.device)
+        mc = int(hdl.multicast_ptr) if (self.use_multicast and hdl.has_multicast_support) else 0
+        hdl.barrier(channel=0)          # every peer is done reading the previous contents
+        pim_ops.spmm_run_dense_peers(self.locals[0].sp_info_ptr, B, [int(p) for p in hdl.buffer_ptrs], mc,
+                                     self.hidden_size, self.r0)
+        hdl.barrier(channel=1)          # every rank's rows have landed everywhere
+        return buf
 
     def _sub_block_views(self, out: torch.Tensor, k: int):
         """Rows of sub-block k of every rank, as views of the full result."""
@@ -114,6 +145,12 @@ class ShardedSpMM:
     def mul(self, B: torch.Tensor, out: Optional[torch.Tensor] = None, gather: bool = True) -> torch.Tensor:
         """Returns the full [N x H] result (on B's device) when `gather`, else a view of the local block."""
         assert B.size(1) == self.hidden_size
+        if self.fused and gather:
+            res = self._mul_fused(B)      # the symmetric buffer IS the result (valid until the next mul)
+            if out is not None:
+                out.copy_(res)
+                return out
+            return res
         if out is None:
             out = torch.empty((self.nrows, self.hidden_size), dtype=B.dtype, device=B.device)
         mine = out[self.r0:self.r1]

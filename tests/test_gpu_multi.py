@@ -29,12 +29,15 @@ def _worker(rank, world, port, ret):
             x = graphgen.reference_features(n, hidden, dtype, seed=1)
             args = types.SimpleNamespace(data_type=dtype, sp_format="CSR", hidden_size=hidden, sp_parts=1, ds_parts=1)
             want = O.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy())
-            for chunks in (1, 3):
-                op = ShardedSpMM(adj.to("cuda"), args, chunks=chunks)
-                for _ in range(2):
+            for kw in (dict(chunks=1), dict(chunks=3), dict(fused=True, use_multicast=False), dict(fused=True)):
+                op = ShardedSpMM(adj.to("cuda"), args, **kw)
+                for _ in range(3):
                     out = op.mul(x.cuda())
                 torch.cuda.synchronize()
-                ok = ok and bool(np.array_equal(out.cpu().numpy(), want))
+                good = bool(np.array_equal(out.cpu().numpy(), want))
+                if not good:
+                    print("rank", rank, "mismatch", dtype, hidden, kw, flush=True)
+                ok = ok and good
                 op.free()
         ret[rank] = ok
         pim_ops.dpu_release()
