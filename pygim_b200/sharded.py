@@ -119,22 +119,33 @@ class ShardedSpMM:
 
     # -- fused all-gather: symmetric result buffer + peer stores from the kernel epilogue
     def _symmetric_out(self, dtype: torch.dtype, device: torch.device):
+        """Two symmetric result buffers per dtype, used alternately."""
         if dtype not in self._symm:
             import torch.distributed._symmetric_memory as symm_mem
             group = self.group if self.group is not None else dist.group.WORLD
-            buf = symm_mem.empty((self.nrows, self.hidden_size), dtype=dtype, device=device)
-            hdl = symm_mem.rendezvous(buf, group.group_name)
-            self._symm[dtype] = (buf, hdl)
+            pair = []
+            for _ in range(2):
+                buf = symm_mem.empty((self.nrows, self.hidden_size), dtype=dtype, device=device)
+                hdl = symm_mem.rendezvous(buf, group.group_name)
+                mc = int(hdl.multicast_ptr) if (self.use_multicast and hdl.has_multicast_support) else 0
+                pair.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs], mc))
+            self._symm[dtype] = [pair, 0]
+            pair[0][1].barrier(channel=0)     # both buffers exist everywhere before the first remote store
         return self._symm[dtype]
 
     def _mul_fused(self, B: torch.Tensor) -> torch.Tensor:
+        """SpMM whose epilogue stores this rank's rows into every peer's buffer; ONE barrier per call.
+
+        Double buffering makes the leading barrier unnecessary: call k writes buffer k%2, whose previous
+        contents (call k-2) every rank finished consuming before it enqueued call k-1 - and every rank passed
+        call k-1's trailing barrier before any rank can start call k.  The returned buffer stays valid until
+        the call after next."""
         from .backend_pim import pim_ops
-        buf, hdl = self._symmetric_out(B.dtype, B.device)
-        mc = int(hdl.multicast_ptr) if (self.use_multicast and hdl.has_multicast_support) else 0
-        hdl.barrier(channel=0)          # every peer is done reading the previous contents
-        pim_ops.spmm_run_dense_peers(self.locals[0].sp_info_ptr, B, [int(p) for p in hdl.buffer_ptrs], mc,
-                                     self.hidden_size, self.r0)
-        hdl.barrier(channel=1)          # every rank's rows have landed everywhere
+        state = self._symmetric_out(B.dtype, B.device)
+        buf, hdl, ptrs, mc = state[0][state[1]]
+        state[1] ^= 1
+        pim_ops.spmm_run_dense_peers(self.locals[0].sp_info_ptr, B, ptrs, mc, self.hidden_size, self.r0)
+        hdl.barrier(channel=0)          # every rank's rows have landed everywhere
         return buf
 
     def _sub_block_views(self, out: torch.Tensor, k: int):
