@@ -420,6 +420,83 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ====================================================================================== inference workload
+def run_inference(a):
+    """BASELINE.json configs[3]: 2-layer GCN / GIN / SAGE end to end on the Reddit-shaped graph, hidden 128 -
+    GPU aggregation (libbackend_pim.so) + torch Linear/BatchNorm on the GPU.  The reference's `--version=cpu`
+    run (aggregation = row-parallel CSR SpMM on the host cores, dense layers = torch CPU) is timed beside it."""
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from pygim_b200 import graphgen
+    from pygim_b200.backend_pim import pim_ops
+    from pygim_b200.backend_pim.spmm import TORCH_TYPES, prepare_pim_spmm
+    from pygim_b200.models import GCN, GIN, SAGE
+    torch.cuda.set_device(0)
+    dtype = TORCH_TYPES[a.dtype]
+    hidden = a.hidden[0] if a.hidden else 128
+    n, nnz, max_deg = graphgen.SHAPES[a.shape]
+    rowptr, col = graphgen.synthetic_csr(n, nnz, max_deg, seed=0, device="cuda")
+    from pygim_b200.sparse_tensor import SparseTensor
+    adj = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(n, n), is_sorted=True)
+    pim_ops.dpu_init_ranks(1)
+    info = pim_ops.device_info()
+    ns = make_args(hidden, dtype, a.format)
+    ns.ds_parts = a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, hidden, info, torch.empty((), dtype=dtype).element_size())
+    A = prepare_pim_spmm(adj, ns)
+    feats, classes = 602, 41                                      # Reddit's feature / class counts
+    torch.manual_seed(0)
+    x = torch.randn(n, feats, device="cuda")
+    results = {}
+    for name, net in (("gcn", GCN), ("gin", GIN), ("sage", SAGE)):
+        model = net(feats, hidden, classes, 2).cuda().eval()
+        with torch.no_grad():
+            for _ in range(max(a.warmup, 3)):
+                model(x, A)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                y = model(x, A)
+            e1.record()
+            torch.cuda.synchronize()
+        results[name] = {"gpu_infer_ms": e0.elapsed_time(e1) / a.steps, "finite": bool(torch.isfinite(y).all())}
+    cpu = None
+    if not a.no_cpu:
+        from oracle import oracle as O
+        O.build()
+        native = O.build_native()
+        clib = O.lib(native) if native else O.lib()
+        threads = O.max_threads()
+        rp_h, cl_h = rowptr.cpu().numpy().astype("int32"), col.cpu().numpy().astype("int32")
+
+        class CpuAdj:      # the torch_sparse.matmul branch of the reference's conv layers (float, 2^19 grid)
+            dtype = torch.float
+
+            def mul(self, xq):
+                return torch.from_numpy(O.spmm_csr_rowpar(rp_h, cl_h, None, xq.numpy(), nthreads=threads, clib=clib))
+
+        torch.set_num_threads(threads)
+        xc = x.cpu()
+        cpu = {"cores": threads, "kind": "port", "unit": "ms",
+               "sample": "one full forward pass per model (whole Reddit-shaped graph), after one warm-up pass"}
+        for name, net in (("gcn", GCN), ("gin", GIN), ("sage", SAGE)):
+            model = net(feats, hidden, classes, 2).eval()
+            with torch.no_grad():
+                model(xc, CpuAdj())
+                t0 = time.perf_counter()
+                model(xc, CpuAdj())
+                cpu[name] = (time.perf_counter() - t0) * 1e3
+    total = sum(r["gpu_infer_ms"] for r in results.values())
+    line = {"metric": "infer_ms_gcn+gin+sage", "value": total, "unit": "ms", "n_gpus": 1, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": total, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": "inference.py 2-layer GCN/GIN/SAGE, %s-shape, hidden %d, %s %s aggregation"
+                                   % (a.shape, hidden, a.dtype, a.format), "nodes": n, "edges": nnz},
+            "per_model": results, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -439,8 +516,12 @@ def main():
                     help="N > 1: all-gather fused into the kernel epilogue (peer stores) or a separate NCCL collective")
     ap.add_argument("--no-multicast", action="store_true", help="fused gather: per-peer stores instead of multimem.st")
     ap.add_argument("--chunks", type=int, default=1, help="N > 1: sub-blocks per rank (all-gather/compute overlap)")
+    ap.add_argument("--workload", default="spmm", choices=["spmm", "inference"],
+                    help="spmm = the headline hidden sweep; inference = 2-layer GCN/GIN/SAGE end to end (configs[3])")
     a = ap.parse_args()
-    if a.impl == "reference":
+    if a.workload == "inference" and a.impl == "ours":
+        run_inference(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
