@@ -246,6 +246,10 @@ def run_ours(a):
         ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj, chunks=a.chunks,
                               fused=(a.gather == "fused"), use_multicast=not a.no_multicast) for h in sweep}
         plans = {h: ops[h].locals[0] for h in sweep}
+    if a.general_kernel:     # force the weighted kernels although the adjacency is value-less (all ones)
+        for h in sweep:
+            for op in ops[h].locals:
+                pim_ops.plan_set_option(op.sp_info_ptr, "unit_values", 0)
     x_dev = {h: graphgen.reference_features(n, h, dtype, seed=h, device=str(dev)) for h in sweep}
     # full outputs (every rank ends with all rows, ready for the next layer)
     c_full = {h: torch.empty((n, h), dtype=dtype, device=dev) for h in sweep}
@@ -400,6 +404,8 @@ def run_ours(a):
         "config": {"workload": "%s-shape %s %s SpMM, hidden sweep %s" % (a.shape, a.dtype, a.format,
                                                                          "/".join(map(str, sweep))),
                    "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": a.format, "sp_parts": 1,
+                   "values": "all ones (value-less adjacency); " + ("general weighted kernel forced" if a.general_kernel
+                             else "unit-value fast path: value stream not read, results bit-identical"),
                    "ds_parts": {str(h): ds_parts[h] for h in sweep},
                    "sharding": ("rows by nnz over %d GPUs, B replicated, all-gather of C %s, inside the timing"
                                 % (world, "fused into the kernel epilogue (NVLink peer stores)" if a.gather == "fused"
@@ -516,6 +522,8 @@ def main():
                     help="N > 1: all-gather fused into the kernel epilogue (peer stores) or a separate NCCL collective")
     ap.add_argument("--no-multicast", action="store_true", help="fused gather: per-peer stores instead of multimem.st")
     ap.add_argument("--chunks", type=int, default=1, help="N > 1: sub-blocks per rank (all-gather/compute overlap)")
+    ap.add_argument("--general-kernel", action="store_true",
+                    help="do not use the unit-value fast path (the adjacency of the benchmark is value-less => ones)")
     ap.add_argument("--workload", default="spmm", choices=["spmm", "inference"],
                     help="spmm = the headline hidden sweep; inference = 2-layer GCN/GIN/SAGE end to end (configs[3])")
     a = ap.parse_args()

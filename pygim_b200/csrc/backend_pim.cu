@@ -97,6 +97,7 @@ struct SparsePart {
     const int *colind = nullptr;
     const void *values = nullptr;
     bool owned = false;            // true: uploaded by us, freed in free_group
+    bool unit_values = false;      // every stored value == 1 (checked on the device at plan time)
     // CSR second-level balancing (built from rowptr on the host)
     std::vector<int> h_rowptr;     // host copy (kept for re-planning when seg_len changes)
     Seg *d_segs = nullptr;
@@ -115,6 +116,7 @@ struct Group {
     std::vector<long long> dense_cols;
     // options (< 0 = automatic)
     long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1, opt_rows_per_ticket = -1;
+    long long opt_unit_values = -1;   // 0 forces the general (weighted) kernels
     // dynamic work distribution of the persistent CSR kernel: a device ticket counter that only grows
     unsigned long long *d_ticket = nullptr;
     unsigned long long ticket_base = 0;
@@ -216,6 +218,17 @@ static void destroy_group(Group *g) {
     delete g;
 }
 
+static cudaError_t dispatch_all_ones(int dtype, const void *val, long long n, int *flag) {
+    switch (dtype) {
+        case PYGIM_INT8: return check_all_ones_i8(val, n, flag, nullptr);
+        case PYGIM_INT16: return check_all_ones_i16(val, n, flag, nullptr);
+        case PYGIM_INT32: return check_all_ones_i32(val, n, flag, nullptr);
+        case PYGIM_INT64: return check_all_ones_i64(val, n, flag, nullptr);
+        case PYGIM_FLT32: return check_all_ones_f32(val, n, flag, nullptr);
+        default: return check_all_ones_f64(val, n, flag, nullptr);
+    }
+}
+
 template <typename L> static cudaError_t dispatch_csr(int dtype, const L &l, int64_t *n) {
     switch (dtype) {
         case PYGIM_INT8: return launch_csr_i8(l, n);
@@ -283,6 +296,7 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.ldc = ldc;
         l.ldp = ldp;
         l.accumulate = accumulate ? 1 : 0;
+        l.unit_values = (p.unit_values && g->opt_unit_values != 0) ? 1 : 0;
         l.n_peers = peers ? peers->n : 0;
         l.mc = (peers && peers->mc) ? peers->mc + peer_off : nullptr;
         for (int q = 0; q < 8; ++q) l.peers[q] = (peers && q < peers->n) ? peers->ptr[q] + peer_off : nullptr;
@@ -304,6 +318,7 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.ldb = ldb;
         l.ldc = ldc;
         l.chunk_nnz = (int)g->opt_chunk_nnz;
+        l.unit_values = (p.unit_values && g->opt_unit_values != 0) ? 1 : 0;
         l.accumulate = accumulate ? 1 : 0;
         l.n_warp_slots = g_ctx.sm_count * (g_ctx.max_threads_per_sm / 32);
         l.sm_count = g_ctx.sm_count;
@@ -460,6 +475,17 @@ PYGIM_API int pygim_spmm_to_device_group(int format, int dtype, int n_sp, const 
             p.colind = colind[i];
             p.values = values[i];
         }
+        {   // unit-value detection (device-side scan of the values as they will be read)
+            int *d_flag = nullptr, h_flag = 1;
+            cudaError_t e = cudaMalloc(&d_flag, sizeof(int));
+            if (e == cudaSuccess) e = cudaMemcpy(d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = dispatch_all_ones(dtype, p.values, p.nnz, d_flag);
+            if (e == cudaSuccess) e = cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+            if (d_flag) cudaFree(d_flag);
+            if (e != cudaSuccess)
+                return bail(fail(PYGIM_ERR_CUDA, "unit-value scan of sparse part %d failed: %s", i, cudaGetErrorString(e)));
+            p.unit_values = (h_flag == 1) && p.nnz > 0;
+        }
         if (format == PYGIM_CSR) {
             p.h_rowptr.resize((size_t)nrows[i] + 1);
             if (mem == PYGIM_MEM_HOST) {
@@ -516,6 +542,8 @@ PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int6
         g->opt_chunk_nnz = value;
     } else if (!std::strcmp(key, "rows_per_ticket")) {
         g->opt_rows_per_ticket = value;
+    } else if (!std::strcmp(key, "unit_values")) {
+        g->opt_unit_values = value;
     } else {
         return fail(PYGIM_ERR_INVALID, "unknown option '%s'", key);
     }

@@ -61,9 +61,10 @@ template <int E, int G> struct CsrTune {
 };
 template <int E, int G> using CooTune = CsrTune<E, G>;   // COO adds a third index stream; same budget works
 
-template <int E, int G> static cudaError_t launch_csr_g(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
+template <int E, int G, bool UNIT>
+static cudaError_t launch_csr_g(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
     auto kernel = csr_spmm_kernel<T, E, G, CsrTune<E, G>::UNROLL, CsrTune<E, G>::MIN_BLOCKS, CsrTune<E, G>::R,
-                                  CsrTune<E, G>::D>;
+                                  CsrTune<E, G>::D, UNIT>;
     static int blocks_per_sm = 0;   // per instantiation
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kCsrThreads, 0);
@@ -111,14 +112,17 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     const long long items = (long long)l.n_seg + l.nrows;
     if (items == 0 || a.nvec == 0) return cudaSuccess;
     cudaError_t err;
+#define PYGIM_CSR_CASE(GV) \
+    case GV: err = l.unit_values ? launch_csr_g<E, GV, true>(a, l, launches) : launch_csr_g<E, GV, false>(a, l, launches); break
     switch (pow2_ceil(a.nvec)) {
-        case 1: err = launch_csr_g<E, 1>(a, l, launches); break;
-        case 2: err = launch_csr_g<E, 2>(a, l, launches); break;
-        case 4: err = launch_csr_g<E, 4>(a, l, launches); break;
-        case 8: err = launch_csr_g<E, 8>(a, l, launches); break;
-        case 16: err = launch_csr_g<E, 16>(a, l, launches); break;
-        default: err = launch_csr_g<E, 32>(a, l, launches); break;
+        PYGIM_CSR_CASE(1);
+        PYGIM_CSR_CASE(2);
+        PYGIM_CSR_CASE(4);
+        PYGIM_CSR_CASE(8);
+        PYGIM_CSR_CASE(16);
+        default: err = l.unit_values ? launch_csr_g<E, 32, true>(a, l, launches) : launch_csr_g<E, 32, false>(a, l, launches); break;
     }
+#undef PYGIM_CSR_CASE
     if (err != cudaSuccess) return err;
     if (l.n_long > 0) {
         FixupArgs<T> f;
@@ -140,14 +144,29 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     return err;
 }
 
+// flag[0] is cleared when any stored value differs from one (plan-time check for the unit-value fast path)
+__global__ void all_ones_kernel(const T *val, long long n, int *flag) {
+    bool ok = true;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        ok = ok && (val[i] == (T)1);
+    if (!ok) *flag = 0;
+}
+
+cudaError_t PYGIM_CAT(check_all_ones_, PYGIM_SFX)(const void *val, long long n, int *d_flag, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    all_ones_kernel<<<1184, 256, 0, stream>>>(static_cast<const T *>(val), n, d_flag);
+    return cudaGetLastError();
+}
+
 cudaError_t PYGIM_CAT(launch_csr_, PYGIM_SFX)(const CsrLaunch &l, int64_t *launches) {
     if (can_vectorize(l.B, l.C, l.ncols, l.ldb, l.ldc, l.ldp)) return launch_csr_e<16 / (int)sizeof(T)>(l, launches);
     return launch_csr_e<1>(l, launches);
 }
 
-template <int E, int G> static cudaError_t launch_coo_g(CooArgs<T> a, const CooLaunch &l, int64_t *launches) {
+template <int E, int G, bool UNIT>
+static cudaError_t launch_coo_g(CooArgs<T> a, const CooLaunch &l, int64_t *launches) {
     auto kernel = coo_spmm_kernel<T, E, G, CooTune<E, G>::UNROLL, CooTune<E, G>::MIN_BLOCKS, CooTune<E, G>::R,
-                                  CooTune<E, G>::D>;
+                                  CooTune<E, G>::D, UNIT>;
     static int blocks_per_sm = 0;   // per instantiation
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kCooThreads, 0);
@@ -198,14 +217,17 @@ template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *la
     chunk = (chunk + 31) / 32 * 32;
     a.chunk_nnz = (int)chunk;
     a.n_chunks = (l.nnz + chunk - 1) / chunk;
+#define PYGIM_COO_CASE(GV) \
+    case GV: return l.unit_values ? launch_coo_g<E, GV, true>(a, l, launches) : launch_coo_g<E, GV, false>(a, l, launches)
     switch (pow2_ceil(a.nvec)) {
-        case 1: return launch_coo_g<E, 1>(a, l, launches);
-        case 2: return launch_coo_g<E, 2>(a, l, launches);
-        case 4: return launch_coo_g<E, 4>(a, l, launches);
-        case 8: return launch_coo_g<E, 8>(a, l, launches);
-        case 16: return launch_coo_g<E, 16>(a, l, launches);
-        default: return launch_coo_g<E, 32>(a, l, launches);
+        PYGIM_COO_CASE(1);
+        PYGIM_COO_CASE(2);
+        PYGIM_COO_CASE(4);
+        PYGIM_COO_CASE(8);
+        PYGIM_COO_CASE(16);
+        default: return l.unit_values ? launch_coo_g<E, 32, true>(a, l, launches) : launch_coo_g<E, 32, false>(a, l, launches);
     }
+#undef PYGIM_COO_CASE
 }
 
 cudaError_t PYGIM_CAT(launch_coo_, PYGIM_SFX)(const CooLaunch &l, int64_t *launches) {

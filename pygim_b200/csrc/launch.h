@@ -23,6 +23,7 @@ struct CsrLaunch {
     long long ncols;          // dense columns of this tile
     long long ldb, ldc, ldp;  // row strides in elements
     int accumulate;
+    int unit_values;          // every stored value is one: skip the value stream (bit-identical result)
     // fused all-gather: n_peers > 0 => rows go to peers[p] + (same offset as C) for every p (C is then unused);
     // mc != NULL => an NVSwitch multicast mapping of the same buffers (one multimem.st instead of n_peers stores)
     void *peers[8];
@@ -43,6 +44,7 @@ struct CooLaunch {
     long long nnz, nrows, ncols;
     long long ldb, ldc;
     int chunk_nnz;            // target nonzeros per warp; <= 0 = automatic
+    int unit_values;
     int accumulate;           // 0: the launcher zero-fills the C tile first
     int n_warp_slots;         // resident warps of the device (for the automatic chunk size)
     int sm_count;
@@ -51,9 +53,10 @@ struct CooLaunch {
     cudaStream_t stream;
 };
 
-#define PYGIM_DECLARE_LAUNCHERS(SFX)                                   \
-    cudaError_t launch_csr_##SFX(const CsrLaunch &l, int64_t *launches); \
-    cudaError_t launch_coo_##SFX(const CooLaunch &l, int64_t *launches);
+#define PYGIM_DECLARE_LAUNCHERS(SFX)                                                                     \
+    cudaError_t launch_csr_##SFX(const CsrLaunch &l, int64_t *launches);                                  \
+    cudaError_t launch_coo_##SFX(const CooLaunch &l, int64_t *launches);                                  \
+    cudaError_t check_all_ones_##SFX(const void *val, long long n, int *d_flag, cudaStream_t stream);
 
 PYGIM_DECLARE_LAUNCHERS(i8)
 PYGIM_DECLARE_LAUNCHERS(i16)

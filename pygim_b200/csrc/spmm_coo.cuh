@@ -93,7 +93,7 @@ __device__ __forceinline__ void coo_flush_row(T *Crow, typename Arith<T>::Acc (&
     for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
 }
 
-template <typename T, int E, int G, int UNROLL, int R, int D>
+template <typename T, int E, int G, int UNROLL, int R, int D, bool UNIT>
 __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long cs, long long ce, int chunk) {
     using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
@@ -129,7 +129,11 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
         for (int r = 0; r < R; ++r) {
             const long long i = cs + d * BATCH + r * 32 + lane;
             nr[d][r] = -1; nc[d][r] = 0; nv[d][r] = 0;
-            if (i < ce) { nr[d][r] = ld_stream(a.rowind + i); nc[d][r] = ld_stream(a.colind + i); nv[d][r] = ld_stream(a.val + i); }
+            if (i < ce) {
+                nr[d][r] = ld_stream(a.rowind + i);
+                nc[d][r] = ld_stream(a.colind + i);
+                if constexpr (!UNIT) nv[d][r] = ld_stream(a.val + i);
+            }
         }
     }
     for (long long base = cs; base < ce; base += BATCH) {
@@ -146,7 +150,11 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
         for (int r = 0; r < R; ++r) {
             const long long i = base + (long long)D * BATCH + r * 32 + lane;
             nr[D - 1][r] = -1; nc[D - 1][r] = 0; nv[D - 1][r] = 0;
-            if (i < ce) { nr[D - 1][r] = ld_stream(a.rowind + i); nc[D - 1][r] = ld_stream(a.colind + i); nv[D - 1][r] = ld_stream(a.val + i); }
+            if (i < ce) {
+                nr[D - 1][r] = ld_stream(a.rowind + i);
+                nc[D - 1][r] = ld_stream(a.colind + i);
+                if constexpr (!UNIT) nv[D - 1][r] = ld_stream(a.val + i);
+            }
         }
         const long long rem = ce - base;
         // whole batch inside the current row?  (sorted stream: first and last entry decide)
@@ -163,7 +171,8 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const Shfl vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
+                    Shfl vv = (Shfl)1;
+                    if constexpr (!UNIT) vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
                     if (active) fma_pack<T, E>(acc, b[u], vv);
                 }
             }
@@ -186,7 +195,8 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
                     for (int s = pos; s < run_end; s += P) {
                         const int src = s + sub;
                         const int cc = __shfl_sync(FULL, c[r], src & 31);
-                        const Shfl vv = __shfl_sync(FULL, v[r], src & 31);
+                        Shfl vv = (Shfl)1;
+                        if constexpr (!UNIT) vv = __shfl_sync(FULL, v[r], src & 31);
                         if (active && src < run_end) {
                             Pack<T, E> b = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
                             fma_pack<T, E>(acc, b, vv);
@@ -202,7 +212,7 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
 }
 
 // Persistent grid; tickets run over col_chunks * n_chunks items, column chunk outermost.
-template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D>
+template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D, bool UNIT>
 __global__ void __launch_bounds__(kCooThreads, MIN_BLOCKS) coo_spmm_kernel(const CooArgs<T> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(kCooThreads, MIN_BLOCKS) coo_spmm_kernel(const
         const long long cs = k * a.chunk_nnz;
         long long ce = cs + a.chunk_nnz;
         if (ce > a.nnz) ce = a.nnz;
-        coo_process_chunk<T, E, G, UNROLL, R, D>(a, cs, ce, chunk);
+        coo_process_chunk<T, E, G, UNROLL, R, D, UNIT>(a, cs, ce, chunk);
     }
 }
 

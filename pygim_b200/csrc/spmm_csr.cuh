@@ -112,7 +112,10 @@ __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, unsigned l
 }
 
 // R = index entries held per lane per batch (a batch is 32*R nonzeros), D = batches prefetched ahead.
-template <typename T, int E, int G, int UNROLL, int R, int D>
+// UNIT: the plan found every stored value equal to one (the value-less adjacency ToSparseTensor yields,
+// spmm.py:36-37) - the value stream is then neither loaded nor shuffled and the FMA degenerates to an add;
+// results are bit-identical to the general path (x * 1 is exact).
+template <typename T, int E, int G, int UNROLL, int R, int D, bool UNIT>
 __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range_start, int range_end, int chunk,
                                                   int dst_row, bool to_partial) {
     using Acc = typename Arith<T>::Acc;
@@ -143,7 +146,10 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
             const int i = range_start + d * BATCH + r * 32 + lane;
             nc[d][r] = 0;
             nv[d][r] = 0;
-            if (i < end) { nc[d][r] = ld_stream(a.colind + i); nv[d][r] = ld_stream(a.val + i); }
+            if (i < end) {
+                nc[d][r] = ld_stream(a.colind + i);
+                if constexpr (!UNIT) nv[d][r] = ld_stream(a.val + i);
+            }
         }
     }
     for (int base = range_start; base < end; base += BATCH) {
@@ -161,7 +167,10 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
             const int i = base + D * BATCH + r * 32 + lane;
             nc[D - 1][r] = 0;
             nv[D - 1][r] = 0;
-            if (i < end) { nc[D - 1][r] = ld_stream(a.colind + i); nv[D - 1][r] = ld_stream(a.val + i); }
+            if (i < end) {
+                nc[D - 1][r] = ld_stream(a.colind + i);
+                if constexpr (!UNIT) nv[D - 1][r] = ld_stream(a.val + i);
+            }
         }
         const int rem = end - base;
         if (rem >= BATCH) {
@@ -177,7 +186,8 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const Shfl vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
+                    Shfl vv = (Shfl)1;
+                    if constexpr (!UNIT) vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
                     if (active) fma_pack<T, E>(acc, b[u], vv);
                 }
             }
@@ -191,7 +201,8 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
                     for (int s = 0; s < steps; ++s) {
                         const int src = s * P + sub;
                         const int cc = __shfl_sync(FULL, c[r], src);
-                        const Shfl vv = __shfl_sync(FULL, v[r], src);
+                        Shfl vv = (Shfl)1;
+                        if constexpr (!UNIT) vv = __shfl_sync(FULL, v[r], src);
                         if (active && src < left) {
                             Pack<T, E> b = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
                             fma_pack<T, E>(acc, b, vv);
@@ -224,7 +235,7 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
 
 // Persistent grid: gridDim.x = resident blocks of the device.  Tickets run over
 // col_chunks * (n_seg + n_row_tickets) items, column chunk outermost.
-template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D>
+template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D, bool UNIT>
 __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const CsrArgs<T> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const
             const int end = __shfl_sync(FULL, cur.rp, j + 1);
             // rows longer than seg_len are covered by their segments + fix-up
             if (cur.to_partial || end - start <= a.seg_len)
-                csr_process_range<T, E, G, UNROLL, R, D>(a, start, end, cur.chunk, cur.first + j, cur.to_partial);
+                csr_process_range<T, E, G, UNROLL, R, D, UNIT>(a, start, end, cur.chunk, cur.first + j, cur.to_partial);
         }
         it = nit;
         cur = nxt;

@@ -126,3 +126,25 @@ def test_sharded_single_rank_and_reddit_like(gpu_backend, oracle):
         torch.cuda.synchronize()
         assert np.array_equal(got.cpu().numpy(), want), (dtype, hidden)
         op.free()
+
+
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+def test_unit_value_fast_path_equals_general_kernel(gpu_backend, oracle, fmt):
+    """A value-less adjacency (=> ones) takes the unit-value kernels; forcing the general kernels on the same
+    plan gives the same bits, and explicit non-unit values never take the fast path."""
+    from pygim_b200.backend_pim import pim_ops
+    from pygim_b200.backend_pim.spmm import prepare_pim_spmm
+    for dtype in (torch.float32, torch.int8, torch.int64):
+        adj = random_adj(300, 300, 0.08, seed=21, long_row=4)
+        x = features(300, 48, dtype, seed=5)
+        want = oracle_spmm(oracle, adj, x, dtype)
+        A = prepare_pim_spmm(adj, make_args(dtype, fmt, 48))
+        fast = A.mul(x)
+        pim_ops.plan_set_option(A.sp_info_ptr, "unit_values", 0)
+        general = A.mul(x)
+        assert torch.equal(fast, want) and torch.equal(general, want), dtype
+        A.free()
+        adj2 = random_adj(300, 300, 0.08, seed=21, value_dtype=dtype, long_row=4)     # mixed values incl. ones
+        A2 = prepare_pim_spmm(adj2, make_args(dtype, fmt, 48))
+        assert torch.equal(A2.mul(x), oracle_spmm(oracle, adj2, x, dtype)), dtype
+        A2.free()
