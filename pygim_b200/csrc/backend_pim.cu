@@ -91,6 +91,17 @@ static int context_init(int device) {
 }
 
 // ------------------------------------------------------------------------------ plans
+// Second-level balancing of a CSR row range: rows longer than seg_len are cut into segments (built on the host
+// from rowptr).  `full` covers every row; the host entry point additionally keeps a few nnz-balanced row chunks
+// so that the download of chunk k overlaps the kernel of chunk k+1.
+struct CsrPlan {
+    long long row_begin = 0, row_end = 0;
+    Seg *d_segs = nullptr;
+    int *d_long_rows = nullptr;
+    int *d_long_seg_ptr = nullptr;
+    int n_seg = 0, n_long = 0;
+};
+
 struct SparsePart {
     long long nrows = 0, ncols = 0, nnz = 0;
     const int *rowidx = nullptr;   // CSR rowptr [nrows+1] or COO rowind [nnz]
@@ -100,10 +111,9 @@ struct SparsePart {
     bool unit_values = false;      // every stored value == 1 (checked on the device at plan time)
     // CSR second-level balancing (built from rowptr on the host)
     std::vector<int> h_rowptr;     // host copy (kept for re-planning when seg_len changes)
-    Seg *d_segs = nullptr;
-    int *d_long_rows = nullptr;
-    int *d_long_seg_ptr = nullptr;
-    int n_seg = 0, n_long = 0, seg_len = 0;
+    CsrPlan full;
+    std::vector<CsrPlan> chunks;   // lazily built by the host entry point
+    int seg_len = 0;
     long long max_row_nnz = 0, empty_rows = 0;
 };
 
@@ -117,6 +127,7 @@ struct Group {
     // options (< 0 = automatic)
     long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1, opt_rows_per_ticket = -1;
     long long opt_unit_values = -1;   // 0 forces the general (weighted) kernels
+    long long opt_host_chunks = -1;   // host entry point: row chunks for download/compute overlap (0 = off)
     // dynamic work distribution of the persistent CSR kernel: a device ticket counter that only grows
     unsigned long long *d_ticket = nullptr;
     unsigned long long ticket_base = 0;
@@ -127,6 +138,9 @@ struct Group {
     void *d_C = nullptr;
     size_t dB_bytes = 0, dC_bytes = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // host entry point: row chunks + a second stream so the download of chunk k overlaps the kernel of chunk k+1
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_done;
     double timers_ms[5] = {0, 0, 0, 0, 0};
     int64_t last_launches = 0;
 };
@@ -140,61 +154,75 @@ static int auto_seg_len(const SparsePart &p) {
     return (int)pow2;
 }
 
-static void free_csr_plan(SparsePart &p) {
-    if (p.d_segs) cudaFree(p.d_segs);
-    if (p.d_long_rows) cudaFree(p.d_long_rows);
-    if (p.d_long_seg_ptr) cudaFree(p.d_long_seg_ptr);
-    p.d_segs = nullptr;
-    p.d_long_rows = nullptr;
-    p.d_long_seg_ptr = nullptr;
-    p.n_seg = p.n_long = 0;
+static void free_plan(CsrPlan &c) {
+    if (c.d_segs) cudaFree(c.d_segs);
+    if (c.d_long_rows) cudaFree(c.d_long_rows);
+    if (c.d_long_seg_ptr) cudaFree(c.d_long_seg_ptr);
+    c = CsrPlan();
 }
 
-// Cut every row longer than seg_len into ceil(nnz/seg_len) near-equal segments.
-static int build_csr_plan(SparsePart &p, int seg_len) {
-    free_csr_plan(p);
-    p.seg_len = seg_len;
+static void free_csr_plan(SparsePart &p) {
+    free_plan(p.full);
+    for (auto &c : p.chunks) free_plan(c);
+    p.chunks.clear();
+}
+
+// Cut every row of [r0, r1) longer than seg_len into ceil(nnz/seg_len) near-equal segments.  Row ids are
+// relative to r0 (the kernel is handed rowptr + r0), nonzero offsets stay absolute.
+static int build_plan_range(const SparsePart &p, int seg_len, long long r0, long long r1, CsrPlan &out) {
+    free_plan(out);
+    out.row_begin = r0;
+    out.row_end = r1;
     std::vector<Seg> segs;
     std::vector<int> long_rows, long_ptr;
     long_ptr.push_back(0);
-    p.max_row_nnz = 0;
-    p.empty_rows = 0;
     const std::vector<int> &rp = p.h_rowptr;
-    for (long long r = 0; r < p.nrows; ++r) {
+    for (long long r = r0; r < r1; ++r) {
         const long long s = (unsigned)rp[r], e = (unsigned)rp[r + 1];
         const long long n = e - s;
-        if (n > p.max_row_nnz) p.max_row_nnz = n;
-        if (n == 0) ++p.empty_rows;
         if (n > seg_len) {
             const long long k = (n + seg_len - 1) / seg_len;
             // equal pieces rounded up to a multiple of 32 so every piece but the last runs full batches
             long long piece = ((n + k - 1) / k + 31) / 32 * 32;
             for (long long b = s; b < e; b += piece) {
                 Seg sg;
-                sg.row = (int)r;
+                sg.row = (int)(r - r0);
                 sg.start = (int)b;
                 sg.end = (int)std::min(e, b + piece);
                 sg.slot = (int)segs.size();
                 segs.push_back(sg);
             }
-            long_rows.push_back((int)r);
+            long_rows.push_back((int)(r - r0));
             long_ptr.push_back((int)segs.size());
         }
     }
-    p.n_seg = (int)segs.size();
-    p.n_long = (int)long_rows.size();
-    if (p.n_seg > 0) {
-        // longest pieces first: the block scheduler hands out blocks in index order
+    out.n_seg = (int)segs.size();
+    out.n_long = (int)long_rows.size();
+    if (out.n_seg > 0) {
+        // longest pieces first: tickets are handed out in index order
         std::stable_sort(segs.begin(), segs.end(),
                          [](const Seg &x, const Seg &y) { return (x.end - x.start) > (y.end - y.start); });
-        CUDA_TRY(cudaMalloc(&p.d_segs, segs.size() * sizeof(Seg)));
-        CUDA_TRY(cudaMemcpy(p.d_segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&p.d_long_rows, long_rows.size() * sizeof(int)));
-        CUDA_TRY(cudaMemcpy(p.d_long_rows, long_rows.data(), long_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&p.d_long_seg_ptr, long_ptr.size() * sizeof(int)));
-        CUDA_TRY(cudaMemcpy(p.d_long_seg_ptr, long_ptr.data(), long_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&out.d_segs, segs.size() * sizeof(Seg)));
+        CUDA_TRY(cudaMemcpy(out.d_segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&out.d_long_rows, long_rows.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(out.d_long_rows, long_rows.data(), long_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&out.d_long_seg_ptr, long_ptr.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(out.d_long_seg_ptr, long_ptr.data(), long_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     return PYGIM_OK;
+}
+
+static int build_csr_plan(SparsePart &p, int seg_len) {
+    free_csr_plan(p);
+    p.seg_len = seg_len;
+    p.max_row_nnz = 0;
+    p.empty_rows = 0;
+    for (long long r = 0; r < p.nrows; ++r) {
+        const long long n = (long long)(unsigned)p.h_rowptr[r + 1] - (long long)(unsigned)p.h_rowptr[r];
+        if (n > p.max_row_nnz) p.max_row_nnz = n;
+        if (n == 0) ++p.empty_rows;
+    }
+    return build_plan_range(p, seg_len, 0, p.nrows, p.full);
 }
 
 static Group *as_group(pygim_handle_t h) { return reinterpret_cast<Group *>(static_cast<uintptr_t>(h)); }
@@ -215,6 +243,9 @@ static void destroy_group(Group *g) {
     if (g->d_C) cudaFree(g->d_C);
     for (auto &e : g->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : g->chunk_done)
+        if (e) cudaEventDestroy(e);
+    if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
     delete g;
 }
 
@@ -258,13 +289,15 @@ struct PeerDst {        // destinations of the fused all-gather (empty => plain 
 };
 
 static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char *C, long long ldc, long long width,
-                    bool accumulate, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0) {
+                    bool accumulate, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0,
+                    const CsrPlan *plan = nullptr) {
     const size_t s = dtype_size(g->dtype);
     cudaError_t err;
     if (g->format == PYGIM_CSR) {
+        const CsrPlan &pl = plan ? *plan : p.full;
         long long ldp = (width * (long long)s + 15) / 16 * 16 / (long long)s;
-        if (p.n_seg > 0) {
-            const size_t need = (size_t)p.n_seg * (size_t)ldp * s;
+        if (pl.n_seg > 0) {
+            const size_t need = (size_t)pl.n_seg * (size_t)ldp * s;
             if (need > g->partial_bytes) {
                 // grow-only scratch; stream-ordered free keeps earlier launches valid
                 if (g->d_partial) CUDA_TRY(cudaFreeAsync(g->d_partial, stream));
@@ -273,18 +306,18 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
             }
         }
         CsrLaunch l;
-        l.rowptr = p.rowidx;
+        l.rowptr = p.rowidx + pl.row_begin;
         l.colind = p.colind;
         l.val = p.values;
         l.B = B;
-        l.C = C;
+        l.C = C + (size_t)pl.row_begin * (size_t)ldc * s;
         l.partial = g->d_partial;
-        l.segs = p.d_segs;
-        l.long_rows = p.d_long_rows;
-        l.long_seg_ptr = p.d_long_seg_ptr;
-        l.n_seg = p.n_seg;
-        l.n_long = p.n_long;
-        l.nrows = (int)p.nrows;
+        l.segs = pl.d_segs;
+        l.long_rows = pl.d_long_rows;
+        l.long_seg_ptr = pl.d_long_seg_ptr;
+        l.n_seg = pl.n_seg;
+        l.n_long = pl.n_long;
+        l.nrows = (int)(pl.row_end - pl.row_begin);
         l.seg_len = p.seg_len;
         // ~256 nonzeros per ticket: one row on Reddit-like graphs, 10 on products-like, 31 on citation graphs
         l.rows_per_ticket = g->opt_rows_per_ticket > 0
@@ -334,11 +367,12 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
 // The (sparse part x dense part) loop of spmm_pim_csr / spmm_host_*_group (ops.hpp:42-62):
 // dense part j of width h_j lands at column offset sum_{k<j} h_k; sparse part 0 overwrites, parts >= 1 add.
 static int run_group_device(Group *g, int n_ds, const void *const *B_parts, const long long *ldb, void *C,
-                            long long ldc, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0) {
+                            long long ldc, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0,
+                            int chunk = -1) {
     if (n_ds != (int)g->dense_cols.size())
         return fail(PYGIM_ERR_INVALID, "expected %d dense parts, got %d", (int)g->dense_cols.size(), n_ds);
     const size_t s = dtype_size(g->dtype);
-    g->last_launches = 0;
+    if (chunk <= 0) g->last_launches = 0;
     long long brow = 0;
     for (size_t i = 0; i < g->parts.size(); ++i) {
         long long ccol = 0;
@@ -346,7 +380,8 @@ static int run_group_device(Group *g, int n_ds, const void *const *B_parts, cons
             const long long w = g->dense_cols[j];
             const char *B = static_cast<const char *>(B_parts[j]) + (size_t)brow * (size_t)ldb[j] * s;
             char *Ct = static_cast<char *>(C) + (size_t)ccol * s;
-            int rc = run_tile(g, g->parts[i], B, ldb[j], Ct, ldc, w, i > 0, stream, peers, peer_off + (size_t)ccol * s);
+            int rc = run_tile(g, g->parts[i], B, ldb[j], Ct, ldc, w, i > 0, stream, peers, peer_off + (size_t)ccol * s,
+                              chunk >= 0 ? &g->parts[i].chunks[chunk] : nullptr);
             if (rc) return rc;
             ccol += w;
         }
@@ -544,6 +579,8 @@ PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int6
         g->opt_rows_per_ticket = value;
     } else if (!std::strcmp(key, "unit_values")) {
         g->opt_unit_values = value;
+    } else if (!std::strcmp(key, "host_chunks")) {
+        g->opt_host_chunks = value;
     } else {
         return fail(PYGIM_ERR_INVALID, "unknown option '%s'", key);
     }
@@ -559,8 +596,8 @@ PYGIM_API int pygim_plan_stats(pygim_handle_t handle, int part, int64_t *out8) {
     out8[1] = p.ncols;
     out8[2] = p.nnz;
     out8[3] = p.max_row_nnz;
-    out8[4] = p.n_long;
-    out8[5] = p.n_seg;
+    out8[4] = p.full.n_long;
+    out8[5] = p.full.n_seg;
     out8[6] = p.seg_len;
     out8[7] = p.empty_rows;
     return PYGIM_OK;
@@ -645,6 +682,32 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
         g->dC_bytes = needC;
     }
     cudaStream_t st = cudaStreamPerThread;
+    // row chunks (CSR, large enough to matter): kernel of chunk k+1 runs while chunk k is downloaded
+    const int kHostChunks = 4;
+    int n_chunks = 1;
+    if (g->format == PYGIM_CSR && g->opt_host_chunks != 0 && rowsC * H * s >= (size_t)(8u << 20) &&
+        g->parts[0].nnz >= 4096) {
+        n_chunks = g->opt_host_chunks > 0 ? (int)g->opt_host_chunks : kHostChunks;
+        if (g->parts[0].chunks.size() != (size_t)n_chunks) {
+            std::vector<int64_t> split((size_t)n_chunks + 1);
+            int rc = pygim_partition_rows_by_nnz(g->parts[0].h_rowptr.data(), g->parts[0].nrows, n_chunks, split.data());
+            if (rc) return rc;
+            for (auto &p : g->parts) {
+                for (auto &c : p.chunks) free_plan(c);
+                p.chunks.assign((size_t)n_chunks, CsrPlan());
+                for (int k = 0; k < n_chunks; ++k) {
+                    rc = build_plan_range(p, p.seg_len, split[k], split[k + 1], p.chunks[k]);
+                    if (rc) return rc;
+                }
+            }
+        }
+        if (!g->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+        while (g->chunk_done.size() < (size_t)n_chunks) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            g->chunk_done.push_back(e);
+        }
+    }
     CUDA_TRY(cudaEventRecord(g->ev[0], st));
     long long col = 0;
     for (int j = 0; j < n_ds; ++j) {   // load_dense: the reference's dpu_broadcast_to (spmm_mul_csr.c:352-367)
@@ -655,13 +718,41 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
         col += (long long)w;
     }
     CUDA_TRY(cudaEventRecord(g->ev[1], st));
-    int rc = pygim_spmm_device(handle, g->d_B, (int64_t)H, g->d_C, (int64_t)H, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(g->ev[2], st));
-    if (rowsC && H)   // retrieve_result (spmm_mul_csr.c:385-410); no merge step follows
-        CUDA_TRY(cudaMemcpy2DAsync(C, (size_t)ldc * s, g->d_C, H * s, H * s, rowsC, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(g->ev[3], st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    // the dense parts are column tiles of the staged B
+    std::vector<const void *> tiles(g->dense_cols.size());
+    std::vector<long long> lds(g->dense_cols.size(), (long long)H);
+    col = 0;
+    for (size_t j = 0; j < g->dense_cols.size(); ++j) {
+        tiles[j] = static_cast<const char *>(g->d_B) + (size_t)col * s;
+        col += g->dense_cols[j];
+    }
+    if (n_chunks == 1) {
+        int rc = run_group_device(g, n_ds, tiles.data(), lds.data(), g->d_C, (long long)H, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(g->ev[2], st));
+        if (rowsC && H)   // retrieve_result (spmm_mul_csr.c:385-410); no merge step follows
+            CUDA_TRY(cudaMemcpy2DAsync(C, (size_t)ldc * s, g->d_C, H * s, H * s, rowsC, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(g->ev[3], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        for (int k = 0; k < n_chunks; ++k) {
+            int rc = run_group_device(g, n_ds, tiles.data(), lds.data(), g->d_C, (long long)H, st, nullptr, 0, k);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(g->chunk_done[k], st));
+            CUDA_TRY(cudaStreamWaitEvent(g->copy_stream, g->chunk_done[k], 0));
+            const CsrPlan &c = g->parts[0].chunks[k];
+            const size_t r0 = (size_t)c.row_begin, nr = (size_t)(c.row_end - c.row_begin);
+            if (nr && H)
+                CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(C) + r0 * (size_t)ldc * s, (size_t)ldc * s,
+                                           static_cast<char *>(g->d_C) + r0 * H * s, H * s, H * s, nr,
+                                           cudaMemcpyDeviceToHost, g->copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(g->ev[2], st));                 // kernels done
+        CUDA_TRY(cudaEventRecord(g->chunk_done[0], g->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, g->chunk_done[0], 0));  // join: ev[3] = last download done
+        CUDA_TRY(cudaEventRecord(g->ev[3], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     float ms = 0;
     g->timers_ms[0] = 0;   // load_sparse: done once in to_device_group
     CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->timers_ms[1] = ms;
