@@ -355,26 +355,44 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel (largest share of the step)
     peak, peak_kind = measured_peaks()
-    dom = max(range(len(sweep)), key=lambda i: per_h_ms[i])
     per_hidden = []
     for i, h in enumerate(sweep):
-        # per-GPU algorithmic bytes of this rank's launch (shard of A and C, all of B)
+        # per-GPU algorithmic bytes of this rank's SpMM (shard of A and C, all of B), A counted once
         b = alg_bytes_csr(r1 - r0, n, shard_nnz, h, esize, a.format)
         per_hidden.append({"hidden": h, "kernel_ms": per_h_ms[i], "gflops": 2.0 * shard_nnz * h / per_h_ms[i] / 1e6,
                            "alg_gbs": b / per_h_ms[i] / 1e6, "frac_hbm": b / per_h_ms[i] / 1e6 / peak,
-                           "gather_gbs": float(esize) * shard_nnz * h / per_h_ms[i] / 1e6})
-    roof = {"bound": "hbm", "kernel": "%s_spmm_kernel<%s> (hidden %d)" % (a.format.lower(), a.dtype, sweep[dom]),
-            "achieved": per_hidden[dom]["alg_gbs"], "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-            "frac": per_hidden[dom]["frac_hbm"], "traffic": None,
-            "alg_bytes_per_launch": alg_bytes_csr(r1 - r0, n, shard_nnz, sweep[dom], esize, a.format),
+                           "gather_gbs": float(esize) * shard_nnz * h / per_h_ms[i] / 1e6,
+                           "launches": ds_parts[h], "tile_cols": h // ds_parts[h]})
+    # The dominant KERNEL is the template instantiation with the largest share of the step.  An instantiation
+    # is fixed by the dense tile a launch handles (G = lanes per tile row), so hidden sizes that run as
+    # several column tiles (H = 128 -> two 64-column launches) are launches of the SAME kernel as H = 64.
+    # Per launch the algorithmic bytes are A + that tile of B + that tile of C (SURVEY.md 8d with H = tile).
+    by_kernel = {}
+    for i, h in enumerate(sweep):
+        w = h // ds_parts[h]
+        k = by_kernel.setdefault(w, {"ms": 0.0, "launches": 0, "bytes": 0.0, "hidden": []})
+        k["ms"] += per_h_ms[i]
+        k["launches"] += ds_parts[h]
+        k["bytes"] += ds_parts[h] * alg_bytes_csr(r1 - r0, n, shard_nnz, w, esize, a.format)
+        k["hidden"].append(h)
+    dom_w = max(by_kernel, key=lambda w: by_kernel[w]["ms"])
+    dk = by_kernel[dom_w]
+    lanes = max(1, min(32, dom_w * esize // 16))
+    roof = {"bound": "hbm",
+            "kernel": "%s_spmm_kernel<%s, G=%d> (%d-column tiles; hidden %s)"
+                      % (a.format.lower(), a.dtype, lanes, dom_w, "/".join(map(str, dk["hidden"]))),
+            "achieved": dk["bytes"] / dk["ms"] / 1e6, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+            "frac": dk["bytes"] / dk["ms"] / 1e6 / peak, "traffic": None,
+            "alg_bytes_per_launch": dk["bytes"] / dk["launches"], "launches_per_step": dk["launches"],
+            "avg_launch_ms": dk["ms"] / dk["launches"], "share_of_step": dk["ms"] / sum(per_h_ms),
             "sweep_achieved": sum(alg_bytes_csr(r1 - r0, n, shard_nnz, h, esize, a.format) for h in sweep)
             / sum(per_h_ms) / 1e6,
-            "note": "Reddit-shape is L2-gather bound (s*nnz*H bytes leave L2 per launch), see DESIGN.md"}
+            "note": "Reddit-shape is L2-gather bound (s*nnz*H bytes leave L2 per launch), see DESIGN.md 4.3"}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path) and (a.shape, a.dtype, a.format, world) == ("reddit", "FLT32", "CSR", 1):
         try:
             with open(traffic_path) as f:
-                roof["traffic"] = json.load(f).get(str(sweep[dom]))
+                roof["traffic"] = json.load(f).get("tile_%d" % dom_w)
         except Exception:
             pass
 

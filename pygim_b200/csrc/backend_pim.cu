@@ -127,6 +127,7 @@ struct Group {
     // options (< 0 = automatic)
     long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1, opt_rows_per_ticket = -1;
     long long opt_unit_values = -1;   // 0 forces the general (weighted) kernels
+    long long opt_short_rows = -1;    // 1/0 force the high-occupancy / deep-unroll CSR instantiation
     long long opt_host_chunks = -1;   // host entry point: row chunks for download/compute overlap (0 = off)
     // dynamic work distribution of the persistent CSR kernel: a device ticket counter that only grows
     unsigned long long *d_ticket = nullptr;
@@ -324,6 +325,8 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
                                 ? (int)g->opt_rows_per_ticket
                                 : (int)std::max<long long>(1, std::min<long long>(31, 256 * std::max<long long>(p.nrows, 1) /
                                                                                      std::max<long long>(p.nnz, 1)));
+        l.short_rows = g->opt_short_rows >= 0 ? (g->opt_short_rows != 0)
+                                              : (p.nnz < 96 * std::max<long long>(p.nrows, 1));
         l.ncols = width;
         l.ldb = ldb;
         l.ldc = ldc;
@@ -579,6 +582,8 @@ PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int6
         g->opt_rows_per_ticket = value;
     } else if (!std::strcmp(key, "unit_values")) {
         g->opt_unit_values = value;
+    } else if (!std::strcmp(key, "short_rows")) {
+        g->opt_short_rows = value;
     } else if (!std::strcmp(key, "host_chunks")) {
         g->opt_host_chunks = value;
     } else {

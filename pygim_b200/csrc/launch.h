@@ -20,6 +20,7 @@ struct CsrLaunch {
     const int *long_seg_ptr;
     int n_seg, n_long, nrows, seg_len;
     int rows_per_ticket;      // consecutive rows one work ticket covers (short-row graphs)
+    int short_rows;           // mean degree is small: prefer the high-occupancy instantiation
     long long ncols;          // dense columns of this tile
     long long ldb, ldc, ldp;  // row strides in elements
     int accumulate;
