@@ -99,6 +99,8 @@ struct CsrPlan {
     Seg *d_segs = nullptr;
     int *d_long_rows = nullptr;
     int *d_long_seg_ptr = nullptr;
+    int *d_seg_count = nullptr;     // arrival counters, [count_chunks x n_long], zero between launches
+    int count_chunks = 0;
     int n_seg = 0, n_long = 0;
 };
 
@@ -159,6 +161,7 @@ static void free_plan(CsrPlan &c) {
     if (c.d_segs) cudaFree(c.d_segs);
     if (c.d_long_rows) cudaFree(c.d_long_rows);
     if (c.d_long_seg_ptr) cudaFree(c.d_long_seg_ptr);
+    if (c.d_seg_count) cudaFree(c.d_seg_count);
     c = CsrPlan();
 }
 
@@ -187,7 +190,7 @@ static int build_plan_range(const SparsePart &p, int seg_len, long long r0, long
             long long piece = ((n + k - 1) / k + 31) / 32 * 32;
             for (long long b = s; b < e; b += piece) {
                 Seg sg;
-                sg.row = (int)(r - r0);
+                sg.long_idx = (int)long_rows.size();
                 sg.start = (int)b;
                 sg.end = (int)std::min(e, b + piece);
                 sg.slot = (int)segs.size();
@@ -291,11 +294,22 @@ struct PeerDst {        // destinations of the fused all-gather (empty => plain 
 
 static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char *C, long long ldc, long long width,
                     bool accumulate, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0,
-                    const CsrPlan *plan = nullptr) {
+                    CsrPlan *plan = nullptr) {
     const size_t s = dtype_size(g->dtype);
     cudaError_t err;
     if (g->format == PYGIM_CSR) {
-        const CsrPlan &pl = plan ? *plan : p.full;
+        CsrPlan &pl = plan ? *plan : p.full;
+        if (pl.n_long > 0) {
+            // one arrival counter per (column chunk, long row); a column chunk is at most 32 words wide
+            const int chunks_needed = (int)((width + 31) / 32);
+            if (chunks_needed > pl.count_chunks) {
+                if (pl.d_seg_count) CUDA_TRY(cudaFreeAsync(pl.d_seg_count, stream));
+                const size_t bytes = (size_t)chunks_needed * (size_t)pl.n_long * sizeof(int);
+                CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&pl.d_seg_count), bytes, stream));
+                CUDA_TRY(cudaMemsetAsync(pl.d_seg_count, 0, bytes, stream));
+                pl.count_chunks = chunks_needed;
+            }
+        }
         long long ldp = (width * (long long)s + 15) / 16 * 16 / (long long)s;
         if (pl.n_seg > 0) {
             const size_t need = (size_t)pl.n_seg * (size_t)ldp * s;
@@ -316,6 +330,7 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.segs = pl.d_segs;
         l.long_rows = pl.d_long_rows;
         l.long_seg_ptr = pl.d_long_seg_ptr;
+        l.seg_count = pl.d_seg_count;
         l.n_seg = pl.n_seg;
         l.n_long = pl.n_long;
         l.nrows = (int)(pl.row_end - pl.row_begin);

@@ -123,6 +123,10 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.C = static_cast<T *>(l.C);
     a.partial = static_cast<T *>(l.partial);
     a.segs = l.segs;
+    a.long_rows = l.long_rows;
+    a.long_seg_ptr = l.long_seg_ptr;
+    a.seg_count = l.seg_count;
+    a.n_long = l.n_long;
     a.n_seg = l.n_seg;
     a.nrows = l.nrows;
     a.seg_len = l.seg_len;
@@ -150,24 +154,6 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
         default: err = l.unit_values ? launch_csr_g<E, 32, true>(a, l, launches) : launch_csr_g<E, 32, false>(a, l, launches); break;
     }
 #undef PYGIM_CSR_CASE
-    if (err != cudaSuccess) return err;
-    if (l.n_long > 0) {
-        FixupArgs<T> f;
-        f.partial = a.partial;
-        f.C = a.C;
-        f.long_rows = l.long_rows;
-        f.long_seg_ptr = l.long_seg_ptr;
-        f.ldp = l.ldp;
-        f.ldc = l.ldc;
-        f.ncols = (int)l.ncols;
-        f.accumulate = l.accumulate;
-        f.n_peers = l.n_peers;      // the fix-up uses the unicast mappings (scalar stores)
-        for (int p = 0; p < kMaxPeers; ++p) f.peers[p] = a.peers[p];
-        const int threads = l.ncols >= 128 ? 128 : (l.ncols > 32 ? 64 : 32);
-        csr_fixup_kernel<T><<<l.n_long, threads, 0, l.stream>>>(f);
-        ++*launches;
-        err = cudaGetLastError();
-    }
     return err;
 }
 

@@ -18,6 +18,7 @@ struct CsrLaunch {
     const Seg *segs;
     const int *long_rows;
     const int *long_seg_ptr;
+    int *seg_count;           // [ceil(ncols/32) x n_long] zeroed arrival counters of the long rows
     int n_seg, n_long, nrows, seg_len;
     int rows_per_ticket;      // consecutive rows one work ticket covers (short-row graphs)
     int short_rows;           // mean degree is small: prefer the high-occupancy instantiation

@@ -20,7 +20,8 @@
 //    the row is written once with a streaming store - no host merge (memcpy_2D / memadd_2D,
 //    spmm_mul_csr.c:41-86) remains.
 //
-// Segment items write to a partial buffer; csr_fixup_kernel adds a row's partials in segment order.
+// Segment items write to a partial buffer; the last segment of a row to finish adds the row's partials in
+// segment order and writes the row (no second kernel, no floating-point atomics).
 #pragma once
 #include "vec.cuh"
 
@@ -29,10 +30,10 @@ namespace pygim {
 constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
 
 struct Seg {       // one nnz-bounded piece of a long row
-    int row;
+    int long_idx;  // which long row (index into long_rows / long_seg_ptr)
     int start;     // first nonzero (index into colind/val)
     int end;       // one past the last nonzero
-    int slot;      // row of the partial buffer this piece writes
+    int slot;      // row of the partial buffer this piece writes (slots of one row are consecutive)
 };
 
 template <typename T> struct CsrArgs {
@@ -43,6 +44,10 @@ template <typename T> struct CsrArgs {
     T *C;              // output, row stride ldc elements
     T *partial;        // [n_seg x ldp] scratch for segment items
     const Seg *segs;
+    const int *long_rows;       // [n_long] row id of every long row
+    const int *long_seg_ptr;    // [n_long + 1] slots of long row i are [ptr[i], ptr[i+1])
+    int *seg_count;             // [col_chunks x n_long] arrival counters, zero between launches
+    int n_long;
     unsigned long long *ticket;      // monotonically increasing work counter (never reset)
     unsigned long long ticket_base;  // its value when this launch starts
     int n_seg;
@@ -81,6 +86,7 @@ __device__ __forceinline__ void st_peers(T *const *peers, int n_peers, T *mc, lo
 }
 
 struct CsrItem {
+    int long_idx;      // segment: its long row; rows: -1
     int first;         // segment: slot of the partial buffer; rows: first row of the ticket
     int count;         // rows covered (1 for a segment)
     int rp;            // rows: lane l holds rowptr[first + l] (l <= count); segment: lane 0 start, lane 1 end
@@ -98,11 +104,13 @@ __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, unsigned l
     const long long k = (long long)(it % items);
     if (k < a.n_seg) {
         const Seg sg = a.segs[k];
+        r.long_idx = sg.long_idx;
         r.first = sg.slot;
         r.count = 1;
         r.rp = lane == 0 ? sg.start : sg.end;
         r.to_partial = true;
     } else {
+        r.long_idx = -1;
         r.first = (int)(k - a.n_seg) * a.rows_per_ticket;
         r.count = min(a.rows_per_ticket, a.nrows - r.first);
         r.rp = a.rowptr[min(r.first + lane, a.nrows)];
@@ -111,13 +119,50 @@ __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, unsigned l
     return r;
 }
 
+// A segment of a long row has just published its partial sum.  The LAST segment of the row to arrive adds the
+// row's partials in slot order (fixed order => bitwise reproducible, no floating-point atomics) and writes the
+// final row.  Out of line on purpose: it runs once per segment and must not cost the gather loop registers.
+template <typename T, int E, int G>
+__device__ __noinline__ void csr_finish_long_row(const CsrArgs<T> &a, int chunk, int long_idx) {
+    using Acc = typename Arith<T>::Acc;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int vec = chunk * G + (lane % G);
+    const bool active = vec < a.nvec;
+    __threadfence();
+    __syncwarp();
+    int *counter = a.seg_count + (long long)chunk * a.n_long + long_idx;
+    int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(counter, 1);
+    arrived = __shfl_sync(FULL, arrived, 0);
+    const int s0 = a.long_seg_ptr[long_idx], s1 = a.long_seg_ptr[long_idx + 1];
+    if (arrived != s1 - s0 - 1) return;
+    __threadfence();
+    if (lane == 0) *counter = 0;          // ready for the next launch
+    if (!(sub == 0 && active)) return;
+    Acc acc[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+    for (int s = s0; s < s1; ++s)
+        add_old<T, E>(acc, ld_cg<T, E>(a.partial + (long long)s * a.ldp + (long long)vec * E));
+    const long long off = (long long)a.long_rows[long_idx] * a.ldc + (long long)vec * E;
+    if (a.n_peers > 0) {
+        st_peers<T, E>(a.peers, a.n_peers, a.mc, off, narrow<T, E>(acc));
+    } else {
+        if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(a.C + off));
+        st_stream<T, E>(a.C + off, narrow<T, E>(acc));
+    }
+}
+
 // R = index entries held per lane per batch (a batch is 32*R nonzeros), D = batches prefetched ahead.
 // UNIT: the plan found every stored value equal to one (the value-less adjacency ToSparseTensor yields,
 // spmm.py:36-37) - the value stream is then neither loaded nor shuffled and the FMA degenerates to an add;
 // results are bit-identical to the general path (x * 1 is exact).
 template <typename T, int E, int G, int UNROLL, int R, int D, bool UNIT>
 __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range_start, int range_end, int chunk,
-                                                  int dst_row, bool to_partial) {
+                                                  int dst_row, int long_idx) {
+    const bool to_partial = long_idx >= 0;
     using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
     constexpr int P = 32 / G;
@@ -219,10 +264,14 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
 #pragma unroll
         for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
     }
-    if (sub == 0 && active) {
-        if (to_partial) {
+    if (to_partial) {
+        if (sub == 0 && active)
             st_plain<T, E>(a.partial + (long long)dst_row * a.ldp + (long long)vec * E, narrow<T, E>(acc));
-        } else if (a.n_peers > 0) {
+        csr_finish_long_row<T, E, G>(a, chunk, long_idx);     // rare path, kept out of line
+        return;
+    }
+    if (sub == 0 && active) {
+        if (a.n_peers > 0) {
             st_peers<T, E>(a.peers, a.n_peers, a.mc, (long long)dst_row * a.ldc + (long long)vec * E,
                            narrow<T, E>(acc));
         } else {
@@ -236,7 +285,7 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
 // Persistent grid: gridDim.x = resident blocks of the device.  Tickets run over
 // col_chunks * (n_seg + n_row_tickets) items, column chunk outermost.
 template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D, bool UNIT>
-__global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const CsrArgs<T> a) {
+__global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const __grid_constant__ CsrArgs<T> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned long long total =
@@ -261,49 +310,10 @@ __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const
             const int end = __shfl_sync(FULL, cur.rp, j + 1);
             // rows longer than seg_len are covered by their segments + fix-up
             if (cur.to_partial || end - start <= a.seg_len)
-                csr_process_range<T, E, G, UNROLL, R, D, UNIT>(a, start, end, cur.chunk, cur.first + j, cur.to_partial);
+                csr_process_range<T, E, G, UNROLL, R, D, UNIT>(a, start, end, cur.chunk, cur.first + j, cur.long_idx);
         }
         it = nit;
         cur = nxt;
-    }
-}
-
-// One block per long row: C[row, :] (+)= sum over the row's segments, in segment order.
-template <typename T> struct FixupArgs {
-    const T *partial;
-    T *C;
-    const int *long_rows;      // [n_long] row ids
-    const int *long_seg_ptr;   // [n_long + 1] slots of row i are [ptr[i], ptr[i+1])
-    long long ldp, ldc;
-    int ncols;
-    int accumulate;
-    T *peers[kMaxPeers];
-    int n_peers;
-};
-
-template <typename T> __global__ void csr_fixup_kernel(const FixupArgs<T> a) {
-    using Acc = typename Arith<T>::Acc;
-    const int i = blockIdx.x;
-    const int row = a.long_rows[i];
-    const int s0 = a.long_seg_ptr[i], s1 = a.long_seg_ptr[i + 1];
-    for (int c = threadIdx.x; c < a.ncols; c += blockDim.x) {
-        Acc acc[1] = {(Acc)0};
-        for (int s = s0; s < s1; ++s) {
-            Pack<T, 1> p;
-            p.e[0] = a.partial[(long long)s * a.ldp + c];
-            add_old<T, 1>(acc, p);
-        }
-        if (a.n_peers > 0) {
-            for (int p = 0; p < a.n_peers; ++p) a.peers[p][(long long)row * a.ldc + c] = (T)acc[0];
-            continue;
-        }
-        T *dst = a.C + (long long)row * a.ldc + c;
-        if (a.accumulate) {
-            Pack<T, 1> o;
-            o.e[0] = *dst;
-            add_old<T, 1>(acc, o);
-        }
-        *dst = (T)acc[0];
     }
 }
 

@@ -43,6 +43,13 @@ template <typename T, int E> __device__ __forceinline__ Pack<T, E> ld_plain(cons
     u.w = *reinterpret_cast<const W *>(p);
     return u.v;
 }
+// L1-bypassing load (ld.global.cg): data another SM wrote during this launch (segment partial sums)
+template <typename T, int E> __device__ __forceinline__ Pack<T, E> ld_cg(const T *p) {
+    using W = typename Word<sizeof(T) * E>::type;
+    union { W w; Pack<T, E> v; } u;
+    u.w = __ldcg(reinterpret_cast<const W *>(p));
+    return u.v;
+}
 // streaming store (evict-first): C rows are written once and not re-read by this kernel
 template <typename T, int E> __device__ __forceinline__ void st_stream(T *p, const Pack<T, E> &v) {
     using W = typename Word<sizeof(T) * E>::type;
