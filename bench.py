@@ -33,6 +33,9 @@ import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes its banner ("NCCL version ...") to STDOUT at the VERSION/INFO levels; rank 0 must print one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 HIDDEN_SWEEP = [16, 32, 64, 128]
 SHAPE = "reddit"
@@ -70,7 +73,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -80,7 +83,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Samples before this point (start-up, warm-up) are not reported."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -91,7 +98,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        for ts, r in self.rows:
+            if ts < t0:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -273,12 +283,13 @@ def run_ours(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
     for _ in range(max(a.warmup, 3)):
         step_device()
     sync()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()               # report only samples taken from here (timed region + e2e region) on
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in sweep]
           for _ in range(a.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,8 +307,6 @@ def run_ours(a):
         t = torch.tensor([elapsed_ms] + per_h_ms, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, per_h_ms = float(t[0]), [float(v) for v in t[1:]]
-    clocks = sampler.stop() if rank == 0 else None
-
     flops_step = sum(2.0 * nnz * h for h in sweep)
     value = flops_step * a.steps / (elapsed_ms * 1e-3) / 1e9
 
@@ -328,6 +337,7 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_value = flops_step * e2e_steps / e2e_s / 1e9
+    clocks = sampler.stop() if rank == 0 else None
     h2d = sum(n * h * esize for h in sweep)
     d2h = sum((r1 - r0) * h * esize for h in sweep)
     timers = {h: pim_ops.last_timers(plans[h].sp_info_ptr) for h in sweep}
