@@ -296,6 +296,8 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
                     bool accumulate, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0,
                     CsrPlan *plan = nullptr) {
     const size_t s = dtype_size(g->dtype);
+    if (ldb < 0 || (unsigned long long)ldb * s >= (1ull << 32))
+        return fail(PYGIM_ERR_INVALID, "row stride of the dense operand must be below 4 GiB");
     cudaError_t err;
     if (g->format == PYGIM_CSR) {
         CsrPlan &pl = plan ? *plan : p.full;

@@ -134,6 +134,7 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.n_row_tickets = (l.nrows + a.rows_per_ticket - 1) / a.rows_per_ticket;
     a.nvec = (int)(l.ncols / E);
     a.ldb = l.ldb;
+    a.ldb_bytes = (unsigned)(l.ldb * (long long)sizeof(T));
     a.ldc = l.ldc;
     a.ldp = l.ldp;
     a.accumulate = l.accumulate;
@@ -208,6 +209,7 @@ template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *la
     a.C = static_cast<T *>(l.C);
     a.nnz = l.nnz;
     a.ldb = l.ldb;
+    a.ldb_bytes = (unsigned)(l.ldb * (long long)sizeof(T));
     a.ldc = l.ldc;
     a.nvec = (int)(l.ncols / E);
     a.accumulate = l.accumulate;

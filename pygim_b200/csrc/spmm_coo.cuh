@@ -39,6 +39,7 @@ template <typename T> struct CooArgs {
     long long nnz;
     long long n_chunks;
     long long ldb, ldc;
+    unsigned ldb_bytes; // ldb * sizeof(T) (< 4 GiB)
     int chunk_nnz;     // nonzeros per work item (multiple of 32)
     int nvec;          // words (of E elements) per dense row
     int col_chunks;    // ceil(nvec / G)
@@ -109,6 +110,7 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
     const bool writer = active && sub == 0;
     const bool accumulate = a.accumulate != 0;
     const T *Bcol = a.B + (long long)vec * E;
+    asm volatile("" : "+l"(Bcol));     // keep the base in a register pair: gather address = one IMAD.WIDE.U32
     T *Ccol = a.C + (long long)vec * E;
 
     // does the neighbouring nonzero belong to the same row as our first / last one?
@@ -167,7 +169,7 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int cc = __shfl_sync(FULL, c[(s0 + u) / G], ((s0 + u) % G) * P + sub);
-                    if (active) b[u] = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+                    if (active) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -198,7 +200,7 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
                         Shfl vv = (Shfl)1;
                         if constexpr (!UNIT) vv = __shfl_sync(FULL, v[r], src & 31);
                         if (active && src < run_end) {
-                            Pack<T, E> b = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+                            Pack<T, E> b = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
                             fma_pack<T, E>(acc, b, vv);
                         }
                     }

@@ -58,6 +58,7 @@ template <typename T> struct CsrArgs {
     int nvec;          // words (of E elements) per dense row
     int col_chunks;    // ceil(nvec / G): every item is processed once per chunk of G words
     long long ldb, ldc, ldp;
+    unsigned ldb_bytes; // ldb * sizeof(T) (< 4 GiB): 32-bit so a gather address is one IMAD.WIDE.U32
     int accumulate;    // 0: C = A*B, 1: C += A*B
     // fused all-gather (row-sharded multi-GPU): when n_peers > 0 every output row is stored to the same
     // offset of every peer's C (NVLink-mapped pointers, the local one included) instead of a.C; when mc is
@@ -175,6 +176,7 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
     const int vec = chunk * G + (lane % G);
     const bool active = vec < a.nvec;
     const T *Bcol = a.B + (long long)vec * E;
+    asm volatile("" : "+l"(Bcol));     // keep the base in a register pair: gather address = one IMAD.WIDE.U32
     const int end = range_end;
 
     Acc acc[E];
@@ -227,7 +229,7 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int cc = __shfl_sync(FULL, c[(s0 + u) / G], ((s0 + u) % G) * P + sub);
-                    if (active) b[u] = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+                    if (active) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -249,7 +251,7 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
                         Shfl vv = (Shfl)1;
                         if constexpr (!UNIT) vv = __shfl_sync(FULL, v[r], src);
                         if (active && src < left) {
-                            Pack<T, E> b = ld_dense<T, E>(Bcol + (long long)cc * a.ldb);
+                            Pack<T, E> b = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
                             fma_pack<T, E>(acc, b, vv);
                         }
                     }

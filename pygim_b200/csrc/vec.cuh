@@ -36,6 +36,12 @@ template <typename T, int E> __device__ __forceinline__ Pack<T, E> ld_dense(cons
     u.w = __ldg(reinterpret_cast<const W *>(p));
     return u.v;
 }
+// Address of this lane's word in dense row `col`: base + col * row_stride_bytes as ONE 32x32->64-bit multiply-add
+// (IMAD.WIDE.U32).  A 64-bit stride costs seven integer instructions per gather in the inner loop.
+template <typename T> __device__ __forceinline__ const T *row_ptr(const T *base, int col, unsigned stride_bytes) {
+    return reinterpret_cast<const T *>(reinterpret_cast<const char *>(base) +
+                                       (unsigned long long)(unsigned)col * stride_bytes);
+}
 // plain load (read-modify-write of C in accumulate mode)
 template <typename T, int E> __device__ __forceinline__ Pack<T, E> ld_plain(const T *p) {
     using W = typename Word<sizeof(T) * E>::type;
