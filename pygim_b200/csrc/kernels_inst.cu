@@ -39,7 +39,7 @@ static int pow2_ceil(long long v) {
 #define PYGIM_CSR_UNROLL 8
 #endif
 #ifndef PYGIM_CSR_MINBLOCKS
-#define PYGIM_CSR_MINBLOCKS 3
+#define PYGIM_CSR_MINBLOCKS 4
 #endif
 #ifndef PYGIM_CSR_PREFETCH
 #define PYGIM_CSR_PREFETCH 2
