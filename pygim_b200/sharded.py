@@ -53,6 +53,52 @@ def all_gather_rows(out: torch.Tensor, row_counts: Sequence[int], mine: torch.Te
             dist.broadcast(chunk, src=ranks[i], group=group)
 
 
+class ColumnShardedSpMM:
+    """C = A @ B with the FEATURE COLUMNS dealt over the ranks (the cross-GPU form of `dense_split`, spmm.py:9-13):
+    every rank holds all of A and computes all rows of its column block C[:, c0:c1] from B[:, c0:c1].  A
+    stand-alone SpMM needs no exchange at all in this form (outputs are concatenated, never summed); `gather=True`
+    all-gathers the column blocks for callers that need the full C everywhere.  Row sharding (ShardedSpMM) is the
+    default because it also divides A's stream; this form is for wide features on graphs whose A is small."""
+
+    def __init__(self, adj: SparseTensor, args, group=None, make_local=None, align: int = 4):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.hidden_size = args.hidden_size
+        self.nrows = adj.size(0)
+        units = -(-self.hidden_size // align)                   # columns are dealt in blocks of `align`
+        per, rest = divmod(units, self.world)
+        bounds = [0]
+        for r in range(self.world):
+            bounds.append(min(self.hidden_size, bounds[-1] + (per + (1 if r < rest else 0)) * align))
+        self.col_splits = bounds
+        self.c0, self.c1 = bounds[self.rank], bounds[self.rank + 1]
+        if make_local is None:
+            from .backend_pim.spmm import prepare_pim_spmm
+            make_local = prepare_pim_spmm
+        local_args = types.SimpleNamespace(**vars(args))
+        local_args.hidden_size = self.c1 - self.c0
+        self.local = make_local(adj, local_args) if self.c1 > self.c0 else None
+
+    def mul(self, B: torch.Tensor, gather: bool = True) -> torch.Tensor:
+        assert B.size(1) == self.hidden_size
+        w = self.c1 - self.c0
+        mine = self.local.mul(B[:, self.c0:self.c1]) if w else B.new_empty((self.nrows, 0))
+        if not gather or self.world == 1:
+            return mine
+        blocks = [B.new_empty((self.nrows, self.col_splits[r + 1] - self.col_splits[r])) for r in range(self.world)]
+        if len({b.size(1) for b in blocks}) == 1 or dist.get_backend(self.group) == "nccl":
+            dist.all_gather(blocks, mine.contiguous(), group=self.group)
+        else:
+            blocks[self.rank].copy_(mine)
+            _gather_views(blocks, self.group)
+        return torch.cat(blocks, dim=1)
+
+    def free(self):
+        if self.local is not None and hasattr(self.local, "free"):
+            self.local.free()
+
+
 def _gather_views(views: Sequence[torch.Tensor], group=None) -> None:
     ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
     for i, v in enumerate(views):

@@ -39,6 +39,14 @@ def _worker(rank, world, port, ret):
                     print("rank", rank, "mismatch", dtype, hidden, kw, flush=True)
                 ok = ok and good
                 op.free()
+        from pygim_b200.sharded import ColumnShardedSpMM
+        x = graphgen.reference_features(n, 48, torch.float32, seed=2)
+        args = types.SimpleNamespace(data_type=torch.float32, sp_format="CSR", hidden_size=48, sp_parts=1, ds_parts=1)
+        cop = ColumnShardedSpMM(adj.to("cuda"), args)
+        out = cop.mul(x.cuda())
+        torch.cuda.synchronize()
+        ok = ok and bool(np.array_equal(out.cpu().numpy(), O.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy())))
+        cop.free()
         ret[rank] = ok
         pim_ops.dpu_release()
     finally:

@@ -26,6 +26,14 @@ class _OracleLocal:
         return out
 
 
+class _OracleLocalOut(_OracleLocal):
+    """Same checker, `mul(B)` returning a new tensor (the surface ColumnShardedSpMM uses)."""
+
+    def mul(self, B, out=None):
+        B = B.contiguous()
+        return super().mul(B, out=torch.empty(self.rowptr.numel() - 1, B.size(1), dtype=B.dtype))
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -40,9 +48,14 @@ def _worker(rank, world, port, ret):
         out = op.mul(x)
         op2 = ShardedSpMM(adj, args, make_local=_OracleLocal, chunks=3)       # overlapped sub-block schedule
         out2 = op2.mul(x)
+        from pygim_b200.sharded import ColumnShardedSpMM
+        op3 = ColumnShardedSpMM(adj, args, make_local=_OracleLocalOut)        # feature-column sharding
+        out3 = op3.mul(x)
+        assert op3.col_splits[-1] == 16 and all(c % 4 == 0 for c in op3.col_splits)
         full = _OracleLocal(adj, args).mul(x, out=torch.empty(n, 16))
         nnz_local = int(op.local_adj.nnz())
-        ret[rank] = (bool(torch.equal(out, full)) and bool(torch.equal(out2, full)), op.splits, nnz_local, adj.nnz())
+        ret[rank] = (bool(torch.equal(out, full)) and bool(torch.equal(out2, full)) and bool(torch.equal(out3, full)),
+                     op.splits, nnz_local, adj.nnz())
     finally:
         dist.destroy_process_group()
 
