@@ -131,9 +131,9 @@ struct Group {
     long long opt_unit_values = -1;   // 0 forces the general (weighted) kernels
     long long opt_short_rows = -1;    // 1/0 force the high-occupancy / deep-unroll CSR instantiation
     long long opt_host_chunks = -1;   // host entry point: row chunks for download/compute overlap (0 = off)
-    // dynamic work distribution of the persistent CSR kernel: a device ticket counter that only grows
+    // dynamic work distribution of the persistent kernels: two device counters (tickets drawn, warps out) that
+    // the last warp of every launch zeroes again
     unsigned long long *d_ticket = nullptr;
-    unsigned long long ticket_base = 0;
     // scratch
     void *d_partial = nullptr;
     size_t partial_bytes = 0;
@@ -355,7 +355,6 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         for (int q = 0; q < 8; ++q) l.peers[q] = (peers && q < peers->n) ? peers->ptr[q] + peer_off : nullptr;
         l.sm_count = g_ctx.sm_count;
         l.ticket = g->d_ticket;
-        l.ticket_base = &g->ticket_base;
         l.stream = stream;
         err = dispatch_csr(g->dtype, l, &g->last_launches);
     } else {
@@ -376,7 +375,6 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.n_warp_slots = g_ctx.sm_count * (g_ctx.max_threads_per_sm / 32);
         l.sm_count = g_ctx.sm_count;
         l.ticket = g->d_ticket;
-        l.ticket_base = &g->ticket_base;
         l.stream = stream;
         err = dispatch_coo(g->dtype, l, &g->last_launches);
     }
@@ -557,8 +555,8 @@ PYGIM_API int pygim_spmm_to_device_group(int format, int dtype, int n_sp, const 
         }
     }
     {
-        cudaError_t ce = cudaMalloc(&g->d_ticket, sizeof(unsigned long long));
-        if (ce == cudaSuccess) ce = cudaMemset(g->d_ticket, 0, sizeof(unsigned long long));
+        cudaError_t ce = cudaMalloc(&g->d_ticket, 2 * sizeof(unsigned long long));
+        if (ce == cudaSuccess) ce = cudaMemset(g->d_ticket, 0, 2 * sizeof(unsigned long long));
         if (ce != cudaSuccess) return bail(fail(PYGIM_ERR_CUDA, "ticket counter setup failed: %s", cudaGetErrorString(ce)));
     }
     for (auto &e : g->ev) {

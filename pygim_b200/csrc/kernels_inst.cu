@@ -77,7 +77,13 @@ template <int E, int G> struct CsrTuneShort {
     static constexpr int D = (R > 1) ? 1 : PYGIM_SHORT_PREFETCH;
     static constexpr int MIN_BLOCKS = (E >= 8) ? PYGIM_NARROW_MINBLOCKS : ((G >= 32) ? PYGIM_CSR_MINBLOCKS : PYGIM_SHORT_MINBLOCKS);
 };
-template <int E, int G> using CooTune = CsrTune<E, G>;
+// COO carries a third index stream and the run walker: one block less per SM than CSR keeps it spill-free
+template <int E, int G> struct CooTune {
+    static constexpr int UNROLL = CsrTune<E, G>::UNROLL;
+    static constexpr int R = CsrTune<E, G>::R;
+    static constexpr int D = CsrTune<E, G>::D;
+    static constexpr int MIN_BLOCKS = CsrTune<E, G>::MIN_BLOCKS > 3 ? 3 : CsrTune<E, G>::MIN_BLOCKS;
+};
 
 
 template <int E, int G, bool UNIT, typename Tune>
@@ -97,10 +103,8 @@ static cudaError_t launch_csr_t(CsrArgs<T> a, const CsrLaunch &l, int64_t *launc
     const unsigned long long blocks_needed = (warps_needed + (kCsrThreads / 32) - 1) / (kCsrThreads / 32);
     if (blocks > blocks_needed) blocks = blocks_needed;
     a.ticket = l.ticket;
-    a.ticket_base = *l.ticket_base;
+    a.n_warps = (unsigned)(blocks * (kCsrThreads / 32));
     kernel<<<(unsigned)blocks, kCsrThreads, 0, l.stream>>>(a);
-    // every warp draws tickets until it sees one past the end: total + (#warps) tickets per launch
-    *l.ticket_base += total + blocks * (kCsrThreads / 32);
     ++*launches;
     return cudaGetLastError();
 }
@@ -193,9 +197,8 @@ static cudaError_t launch_coo_g(CooArgs<T> a, const CooLaunch &l, int64_t *launc
     const unsigned long long blocks_needed = (total + (kCooThreads / 32) - 1) / (kCooThreads / 32);
     if (blocks > blocks_needed) blocks = blocks_needed;
     a.ticket = l.ticket;
-    a.ticket_base = *l.ticket_base;
+    a.n_warps = (unsigned)(blocks * (kCooThreads / 32));
     kernel<<<(unsigned)blocks, kCooThreads, 0, l.stream>>>(a);
-    *l.ticket_base += total + blocks * (kCooThreads / 32);
     ++*launches;
     return cudaGetLastError();
 }

@@ -32,8 +32,7 @@ struct CsrLaunch {
     void *mc;
     int n_peers;
     int sm_count;
-    unsigned long long *ticket;        // device work counter of the plan (monotonic)
-    unsigned long long *ticket_base;   // host mirror: value of *ticket when the next launch starts
+    unsigned long long *ticket;        // two device counters of the plan (work tickets, warps out), zero at rest
     cudaStream_t stream;
 };
 
@@ -51,7 +50,6 @@ struct CooLaunch {
     int n_warp_slots;         // resident warps of the device (for the automatic chunk size)
     int sm_count;
     unsigned long long *ticket;
-    unsigned long long *ticket_base;
     cudaStream_t stream;
 };
 

@@ -24,6 +24,7 @@
 // C is zero-filled by the launcher first (the reference's torch::zeros, pytorch_api.cpp:357-358)
 // unless accumulate is set.
 #pragma once
+#include "spmm_csr.cuh"   // release_tickets
 #include "vec.cuh"
 
 namespace pygim {
@@ -34,8 +35,8 @@ template <typename T> struct CooArgs {
     const T *val;
     const T *B;
     T *C;
-    unsigned long long *ticket;
-    unsigned long long ticket_base;
+    unsigned long long *ticket;      // same self-resetting counters as the CSR kernel (spmm_csr.cuh)
+    unsigned int n_warps;
     long long nnz;
     long long n_chunks;
     long long ldb, ldc;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kCooThreads, MIN_BLOCKS) coo_spmm_kernel(const
     const unsigned long long total = (unsigned long long)a.col_chunks * (unsigned long long)a.n_chunks;
     for (;;) {
         unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.ticket, 1ULL) - a.ticket_base;
+        if (lane == 0) t = atomicAdd(a.ticket, 1ULL);
         t = __shfl_sync(FULL, t, 0);
         if (t >= total) break;
         const int chunk = (int)(t / (unsigned long long)a.n_chunks);
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(kCooThreads, MIN_BLOCKS) coo_spmm_kernel(const
         if (ce > a.nnz) ce = a.nnz;
         coo_process_chunk<T, E, G, UNROLL, R, D, UNIT>(a, cs, ce, chunk);
     }
+    release_tickets(a.ticket, a.n_warps);
 }
 
 }  // namespace pygim

@@ -5,7 +5,7 @@
 // of dense_size*byte_dt bytes per nonzero (:108-126), here:
 //
 //  * the grid is PERSISTENT (resident warps only); every warp pulls work items from a global
-//    ticket counter, so no warp idles while another still owns a long row (the reference's
+//    (self-resetting, CUDA-graph friendly) ticket counter, so no warp idles while another still owns a long row (the reference's
 //    second-level balancing, partition_tsklt_by_nnz_csr, support/partition.c:186-229, made dynamic);
 //  * a work item is a whole row, or - for rows longer than seg_len - one seg_len-bounded segment
 //    of a row; segment items come first in ticket order, longest first;
@@ -48,8 +48,9 @@ template <typename T> struct CsrArgs {
     const int *long_seg_ptr;    // [n_long + 1] slots of long row i are [ptr[i], ptr[i+1])
     int *seg_count;             // [col_chunks x n_long] arrival counters, zero between launches
     int n_long;
-    unsigned long long *ticket;      // monotonically increasing work counter (never reset)
-    unsigned long long ticket_base;  // its value when this launch starts
+    unsigned long long *ticket;      // ticket[0]: work counter, ticket[1]: warps that have left the kernel;
+                                     // both are zero between launches (the last warp out resets them)
+    unsigned int n_warps;            // warps of this launch
     int n_seg;
     int nrows;
     int seg_len;       // rows with more nonzeros than this are handled through segs
@@ -69,6 +70,20 @@ template <typename T> struct CsrArgs {
 };
 
 constexpr int kCsrThreads = 256;
+
+// Every warp calls this once, after it drew its last (failing) ticket: the last warp out zeroes the counters, so
+// the plan needs no host-side bookkeeping between launches and a launch can be replayed from a CUDA graph.
+__device__ __forceinline__ void release_tickets(unsigned long long *ticket, unsigned int n_warps) {
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        const unsigned long long left = atomicAdd(ticket + 1, 1ULL);
+        if (left == (unsigned long long)n_warps - 1ULL) {
+            ticket[0] = 0ULL;
+            ticket[1] = 0ULL;
+            __threadfence();
+        }
+    }
+}
 
 // store one word of an output row to every destination of the fused all-gather
 template <typename T, int E>
@@ -295,7 +310,7 @@ __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const
 
     auto take_ticket = [&]() -> unsigned long long {
         unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.ticket, 1ULL) - a.ticket_base;
+        if (lane == 0) t = atomicAdd(a.ticket, 1ULL);
         return __shfl_sync(FULL, t, 0);
     };
 
@@ -317,6 +332,7 @@ __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const
         it = nit;
         cur = nxt;
     }
+    release_tickets(a.ticket, a.n_warps);
 }
 
 }  // namespace pygim
