@@ -142,7 +142,8 @@ struct Group {
     size_t dB_bytes = 0, dC_bytes = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // host entry point: row chunks + a second stream so the download of chunk k overlaps the kernel of chunk k+1
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // downloads
+    cudaStream_t copy_in_stream = nullptr;   // uploads
     std::vector<cudaEvent_t> chunk_done;
     double timers_ms[5] = {0, 0, 0, 0, 0};
     int64_t last_launches = 0;
@@ -250,6 +251,7 @@ static void destroy_group(Group *g) {
     for (auto &e : g->chunk_done)
         if (e) cudaEventDestroy(e);
     if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+    if (g->copy_in_stream) cudaStreamDestroy(g->copy_in_stream);
     delete g;
 }
 
@@ -677,6 +679,13 @@ PYGIM_API int pygim_spmm_device_peers(pygim_handle_t handle, const void *B, int6
                             static_cast<cudaStream_t>(stream), &dst, 0);
 }
 
+// Host entry point.  Software pipeline over three streams so that PCIe and the kernels overlap:
+//   * every dense part is cut into column tiles of 128 bytes per row (when it is at least 256 bytes wide); tile
+//     t+1 is uploaded (copy-in stream) while tile t is computed, and the finished C tile t is downloaded
+//     (copy-out stream) while tile t+1 is computed;
+//   * the LAST tile (or the only one) is additionally cut into nnz-balanced row chunks (CSR) so that its download
+//     overlaps its own kernels and only the last chunk's copy is exposed.
+// Each tile is staged contiguously on the device ([rowsB x tile_width]), so it is L2 friendly for the gathers.
 PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
                               void *C, int64_t ldc) {
     Group *g = as_group(handle);
@@ -687,8 +696,32 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
     CUDA_TRY(cudaSetDevice(g->device));
     const size_t s = dtype_size(g->dtype);
     const size_t rowsB = (size_t)g->total_cols, rowsC = (size_t)g->total_rows, H = (size_t)g->h_size;
-    // device staging: B as one [rowsB x H] matrix (dense parts side by side), C as [rowsC x H]
-    const size_t needB = std::max<size_t>(rowsB * H * s, 16), needC = std::max<size_t>(rowsC * H * s, 16);
+    const bool pipelined = g->opt_host_chunks != 0 &&
+                           (g->opt_host_chunks > 0 || rowsC * H * s >= (size_t)(8u << 20));
+
+    // ---- column tiles
+    struct Tile { int part; size_t col0, width, dev_off; const char *host; size_t host_ld; };
+    std::vector<Tile> tiles;
+    size_t col = 0, dev_off = 0;
+    for (int j = 0; j < n_ds; ++j) {
+        const size_t w = (size_t)g->dense_cols[j];
+        size_t n_t = 1;
+        if (pipelined && w * s >= 256 && (w * s) % 128 == 0) n_t = w * s / 128;
+        const size_t tw = w / n_t;
+        for (size_t t = 0; t < n_t; ++t) {
+            Tile tl;
+            tl.part = j;
+            tl.col0 = col + t * tw;
+            tl.width = tw;
+            tl.dev_off = dev_off;
+            tl.host = static_cast<const char *>(B_parts[j]) + t * tw * s;
+            tl.host_ld = (size_t)ldb[j];
+            if (tw) tiles.push_back(tl);
+            dev_off += rowsB * tw * s;
+        }
+        col += w;
+    }
+    const size_t needB = std::max<size_t>(dev_off, 16), needC = std::max<size_t>(rowsC * H * s, 16);
     if (needB > g->dB_bytes) {
         if (g->d_B) CUDA_TRY(cudaFree(g->d_B));
         g->d_B = nullptr; g->dB_bytes = 0;
@@ -701,13 +734,11 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
         CUDA_TRY(cudaMalloc(&g->d_C, needC));
         g->dC_bytes = needC;
     }
-    cudaStream_t st = cudaStreamPerThread;
-    // row chunks (CSR, large enough to matter): kernel of chunk k+1 runs while chunk k is downloaded
-    const int kHostChunks = 4;
+
+    // ---- row chunks of the last tile (CSR only: COO chunks are nnz ranges, not row ranges)
     int n_chunks = 1;
-    if (g->format == PYGIM_CSR && g->opt_host_chunks != 0 && rowsC * H * s >= (size_t)(8u << 20) &&
-        g->parts[0].nnz >= 4096) {
-        n_chunks = g->opt_host_chunks > 0 ? (int)g->opt_host_chunks : kHostChunks;
+    if (pipelined && g->format == PYGIM_CSR && g->parts[0].nnz >= 4096 && rowsC >= 64) {
+        n_chunks = g->opt_host_chunks > 0 ? (int)g->opt_host_chunks : 4;
         if (g->parts[0].chunks.size() != (size_t)n_chunks) {
             std::vector<int64_t> split((size_t)n_chunks + 1);
             int rc = pygim_partition_rows_by_nnz(g->parts[0].h_rowptr.data(), g->parts[0].nrows, n_chunks, split.data());
@@ -721,63 +752,83 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
                 }
             }
         }
-        if (!g->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
-        while (g->chunk_done.size() < (size_t)n_chunks) {
-            cudaEvent_t e;
-            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            g->chunk_done.push_back(e);
-        }
     }
+    if (!g->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    if (!g->copy_in_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_in_stream, cudaStreamNonBlocking));
+    while (g->chunk_done.size() < tiles.size() * 2 + (size_t)n_chunks + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g->chunk_done.push_back(e);
+    }
+    cudaStream_t st = cudaStreamPerThread, sin = g->copy_in_stream, sout = g->copy_stream;
+    size_t next_event = 0;
+    auto new_event = [&]() { return g->chunk_done[next_event++]; };
+
+    g->last_launches = 0;
     CUDA_TRY(cudaEventRecord(g->ev[0], st));
-    long long col = 0;
-    for (int j = 0; j < n_ds; ++j) {   // load_dense: the reference's dpu_broadcast_to (spmm_mul_csr.c:352-367)
-        const size_t w = (size_t)g->dense_cols[j];
-        if (w && rowsB)
-            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(g->d_B) + (size_t)col * s, H * s, B_parts[j],
-                                       (size_t)ldb[j] * s, w * s, rowsB, cudaMemcpyHostToDevice, st));
-        col += (long long)w;
+    {   // the copy streams start after everything already queued on the compute stream
+        cudaEvent_t e = new_event();
+        CUDA_TRY(cudaEventRecord(e, st));
+        CUDA_TRY(cudaStreamWaitEvent(sin, e, 0));
+        CUDA_TRY(cudaStreamWaitEvent(sout, e, 0));
     }
-    CUDA_TRY(cudaEventRecord(g->ev[1], st));
-    // the dense parts are column tiles of the staged B
-    std::vector<const void *> tiles(g->dense_cols.size());
-    std::vector<long long> lds(g->dense_cols.size(), (long long)H);
-    col = 0;
-    for (size_t j = 0; j < g->dense_cols.size(); ++j) {
-        tiles[j] = static_cast<const char *>(g->d_B) + (size_t)col * s;
-        col += g->dense_cols[j];
+    std::vector<cudaEvent_t> uploaded(tiles.size());
+    for (size_t t = 0; t < tiles.size(); ++t) {   // load_dense: the reference's dpu_broadcast_to (spmm_mul_csr.c:352-367)
+        const Tile &tl = tiles[t];
+        if (rowsB)
+            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(g->d_B) + tl.dev_off, tl.width * s, tl.host, tl.host_ld * s,
+                                       tl.width * s, rowsB, cudaMemcpyHostToDevice, sin));
+        uploaded[t] = new_event();
+        CUDA_TRY(cudaEventRecord(uploaded[t], sin));
     }
-    if (n_chunks == 1) {
-        int rc = run_group_device(g, n_ds, tiles.data(), lds.data(), g->d_C, (long long)H, st);
-        if (rc) return rc;
+    if (tiles.empty() || rowsC == 0) {
+        CUDA_TRY(cudaEventRecord(g->ev[1], st));
         CUDA_TRY(cudaEventRecord(g->ev[2], st));
-        if (rowsC && H)   // retrieve_result (spmm_mul_csr.c:385-410); no merge step follows
-            CUDA_TRY(cudaMemcpy2DAsync(C, (size_t)ldc * s, g->d_C, H * s, H * s, rowsC, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(g->ev[3], st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-    } else {
-        for (int k = 0; k < n_chunks; ++k) {
-            int rc = run_group_device(g, n_ds, tiles.data(), lds.data(), g->d_C, (long long)H, st, nullptr, 0, k);
-            if (rc) return rc;
-            CUDA_TRY(cudaEventRecord(g->chunk_done[k], st));
-            CUDA_TRY(cudaStreamWaitEvent(g->copy_stream, g->chunk_done[k], 0));
-            const CsrPlan &c = g->parts[0].chunks[k];
-            const size_t r0 = (size_t)c.row_begin, nr = (size_t)(c.row_end - c.row_begin);
-            if (nr && H)
-                CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(C) + r0 * (size_t)ldc * s, (size_t)ldc * s,
-                                           static_cast<char *>(g->d_C) + r0 * H * s, H * s, H * s, nr,
-                                           cudaMemcpyDeviceToHost, g->copy_stream));
+    }
+    for (size_t t = 0; t < tiles.size() && rowsC; ++t) {
+        const Tile &tl = tiles[t];
+        CUDA_TRY(cudaStreamWaitEvent(st, uploaded[t], 0));
+        if (t == 0) CUDA_TRY(cudaEventRecord(g->ev[1], st));          // first tile on the device: kernels start
+        const bool last = t + 1 == tiles.size();
+        const int chunks_here = last ? n_chunks : 1;
+        for (int k = 0; k < chunks_here; ++k) {
+            long long brow = 0;
+            for (size_t i = 0; i < g->parts.size(); ++i) {            // sparse part 0 overwrites, parts >= 1 add
+                SparsePart &p = g->parts[i];
+                const char *Bt = static_cast<const char *>(g->d_B) + tl.dev_off + (size_t)brow * tl.width * s;
+                char *Ct = static_cast<char *>(g->d_C) + tl.col0 * s;
+                int rc = run_tile(g, p, Bt, (long long)tl.width, Ct, (long long)H, (long long)tl.width, i > 0, st, nullptr,
+                                  0, chunks_here > 1 ? &p.chunks[k] : nullptr);
+                if (rc) return rc;
+                brow += p.ncols;
+            }
+            size_t r0 = 0, nr = rowsC;
+            if (chunks_here > 1) {
+                r0 = (size_t)g->parts[0].chunks[k].row_begin;
+                nr = (size_t)(g->parts[0].chunks[k].row_end - g->parts[0].chunks[k].row_begin);
+            }
+            if (last && k + 1 == chunks_here) CUDA_TRY(cudaEventRecord(g->ev[2], st));   // kernels done
+            cudaEvent_t done = new_event();
+            CUDA_TRY(cudaEventRecord(done, st));
+            CUDA_TRY(cudaStreamWaitEvent(sout, done, 0));
+            if (nr)   // retrieve_result (spmm_mul_csr.c:385-410); no merge step follows
+                CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(C) + (r0 * (size_t)ldc + tl.col0) * s, (size_t)ldc * s,
+                                           static_cast<char *>(g->d_C) + (r0 * H + tl.col0) * s, H * s, tl.width * s, nr,
+                                           cudaMemcpyDeviceToHost, sout));
         }
-        CUDA_TRY(cudaEventRecord(g->ev[2], st));                 // kernels done
-        CUDA_TRY(cudaEventRecord(g->chunk_done[0], g->copy_stream));
-        CUDA_TRY(cudaStreamWaitEvent(st, g->chunk_done[0], 0));  // join: ev[3] = last download done
+    }
+    {   // join the copy streams; ev[3] = last download done
+        cudaEvent_t e = new_event();
+        CUDA_TRY(cudaEventRecord(e, sout));
+        CUDA_TRY(cudaStreamWaitEvent(st, e, 0));
         CUDA_TRY(cudaEventRecord(g->ev[3], st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     float ms = 0;
     g->timers_ms[0] = 0;   // load_sparse: done once in to_device_group
-    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->timers_ms[1] = ms;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->timers_ms[2] = ms;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[2], g->ev[3])); g->timers_ms[3] = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->timers_ms[1] = ms;   // exposed part of the upload
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->timers_ms[2] = ms;   // kernels (uploads/downloads overlap)
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[2], g->ev[3])); g->timers_ms[3] = ms;   // exposed tail of the download
     g->timers_ms[4] = 0;   // alignment: none
     return PYGIM_OK;
 }

@@ -146,3 +146,24 @@ def test_cuda_graph_capture_and_replay(gpu_backend, oracle, fmt):
         torch.cuda.synchronize()
         assert torch.equal(out.cpu(), oracle_spmm(oracle, adj, xs, torch.float32)), seed
     A.free()
+
+
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+def test_pipelined_host_entry_point(gpu_backend, oracle, fmt):
+    """Host operands with the upload/compute/download pipeline forced on (column tiles of 128 bytes + row chunks
+    of the last tile), with several sparse and dense parts, 16-byte aligned and unaligned widths."""
+    from pygim_b200.backend_pim import pim_ops
+    from pygim_b200.backend_pim.spmm import prepare_pim_spmm
+    for dtype, hidden, sp, ds in ((torch.float32, 128, 1, 1), (torch.float32, 96, 2, 2), (torch.int8, 256, 1, 1),
+                                  (torch.int32, 72, 3, 1), (torch.float64, 33, 1, 2)):
+        adj = random_adj(700, 700, 0.05, seed=hidden, long_row=9, value_dtype=dtype)
+        x = features(700, hidden, dtype, seed=2)
+        want = oracle_spmm(oracle, adj, x, dtype)
+        A = prepare_pim_spmm(adj, make_args(dtype, fmt, hidden, sp_parts=sp, ds_parts=ds))
+        for chunks in (3, 1, 0):
+            pim_ops.plan_set_option(A.sp_info_ptr, "host_chunks", chunks)
+            out = torch.empty((700, hidden), dtype=dtype).pin_memory()
+            got = A.mul(x.pin_memory(), out=out)
+            assert torch.equal(got, want), (dtype, hidden, sp, ds, chunks)
+            assert torch.equal(A.mul(x), want), (dtype, hidden, sp, ds, chunks, "pageable")
+        A.free()
