@@ -170,7 +170,7 @@ def autotune(adj_or_stats, hidden_size: int, split_set: Optional[Sequence[Tuple[
         if ms < best_ms:
             best, best_ms = cfg, ms
     slots = dev.sm_count * 64
-    seg_len = 256
+    seg_len = 512
     while seg_len < stats.nnz / max(1, slots * 8) and seg_len < 4096:
         seg_len *= 2
     skewed = stats.max_degree > seg_len or stats.cv_degree > 0.5

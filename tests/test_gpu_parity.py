@@ -19,6 +19,9 @@ def _run(front, adj, args, x, **kw):
     else:
         from pygim_b200.backend_pim.spmv import prepare_pim_spmv
         A = prepare_pim_spmv(adj, args)
+    if kw.get("seg_len"):
+        from pygim_b200.backend_pim import pim_ops
+        pim_ops.plan_set_option(A.sp_info_ptr, "seg_len", kw["seg_len"])
     out = A.mul(x)
     if out.is_cuda:
         torch.cuda.synchronize()
@@ -32,7 +35,7 @@ def _run(front, adj, args, x, **kw):
 def test_spmm_all_dtypes_host_operand(gpu_backend, oracle, dtype, fmt, hidden):
     adj = random_adj(301, 301, 0.05, seed=hidden, empty_rows=(0, 7, 300), long_row=5)
     x = features(301, hidden, dtype, seed=1)
-    out = _run("spmm", adj, make_args(dtype, fmt, hidden), x)
+    out = _run("spmm", adj, make_args(dtype, fmt, hidden), x, seg_len=64)     # the 270-nnz row is cut into segments
     assert out.dtype == dtype and out.device.type == "cpu"
     assert torch.equal(out, oracle_spmm(oracle, adj, x, dtype))
 
@@ -67,7 +70,7 @@ def test_int8_overflow_wraps(gpu_backend, oracle):
 
 @pytest.mark.parametrize("fmt", ["CSR", "COO"])
 def test_long_rows_are_segmented(gpu_backend, oracle, fmt):
-    # one row far above seg_len (256 minimum) so the segment + fix-up path runs
+    # one row far above seg_len (512 minimum) so the segment + last-arriver merge path runs
     n = 3000
     adj = random_adj(40, n, 0.01, seed=1, long_row=3)
     for dtype in (torch.float32, torch.int16, torch.float64, torch.int64):
