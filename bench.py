@@ -398,6 +398,21 @@ def run_ours(a):
             "sweep_achieved": sum(alg_bytes_csr(r1 - r0, n, shard_nnz, h, esize, a.format) for h in sweep)
             / sum(per_h_ms) / 1e6,
             "note": "Reddit-shape is L2-gather bound (s*nnz*H bytes leave L2 per launch), see DESIGN.md 4.3"}
+    # secondary bound: the measured ceiling of random row gathers (tools/l2_gather_probe)
+    try:
+        with open(os.path.join(ROOT, "profiles", "gather_ceiling.json")) as f:
+            ceil = json.load(f)
+        row_bytes = dom_w * esize
+        key = str(min((64, 128, 256, 512), key=lambda b: abs(b - row_bytes)))
+        resident = n * row_bytes <= 0.46 * info["l2_bytes"]
+        peak_g = ceil["l2_resident_tbs" if resident else "hbm_served_tbs"][key]
+        ach_g = float(esize) * shard_nnz * sum(h for h in dk["hidden"]) / dk["ms"] / 1e9
+        roof["gather"] = {"bound": "l2-gather" if resident else "hbm-gather", "achieved_tbs": ach_g,
+                          "ceiling_tbs": peak_g, "frac": ach_g / peak_g, "row_bytes": row_bytes,
+                          "what": "s*nnz*H bytes gathered per launch / time, against the measured ceiling of random "
+                                  "row gathers (profiles/r01_l2_gather_probe.txt)"}
+    except Exception:
+        pass
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path) and (a.shape, a.dtype, a.format, world) == ("reddit", "FLT32", "CSR", 1):
         try:
