@@ -256,6 +256,23 @@ def run_ours(a):
         ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj, chunks=a.chunks,
                               fused=(a.gather == "fused"), use_multicast=not a.no_multicast) for h in sweep}
         plans = {h: ops[h].locals[0] for h in sweep}
+        if a.gather == "fused":
+            # the fused path needs NVLink peer mappings (symmetric memory); if this box cannot provide them, every
+            # rank falls back to the NCCL all-gather together and the JSON line says so
+            ok = torch.ones(1, device=dev)
+            try:
+                probe = torch.zeros((n, sweep[0]), dtype=dtype, device=dev)
+                ops[sweep[0]].mul(probe)
+                torch.cuda.synchronize()
+            except Exception as exc:      # noqa: BLE001
+                ok.zero_()
+                if rank == 0:
+                    print("bench.py: fused all-gather unavailable (%s); using NCCL" % str(exc)[:200], file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) == 0.0:
+                a.gather = "nccl"
+                for h in sweep:
+                    ops[h].fused = False
     if a.general_kernel:     # force the weighted kernels although the adjacency is value-less (all ones)
         for h in sweep:
             for op in ops[h].locals:
