@@ -150,7 +150,10 @@ __device__ __noinline__ void csr_finish_long_row(const CsrArgs<T> &a, int chunk,
     __syncwarp();
     int *counter = a.seg_count + (long long)chunk * a.n_long + long_idx;
     int arrived = 0;
-    if (lane == 0) arrived = atomicAdd(counter, 1);
+    if (lane == 0) {
+        __threadfence();          // release: the warp's partial-sum stores (ordered by the barrier above) before the count
+        arrived = atomicAdd(counter, 1);
+    }
     arrived = __shfl_sync(FULL, arrived, 0);
     const int s0 = a.long_seg_ptr[long_idx], s1 = a.long_seg_ptr[long_idx + 1];
     if (arrived != s1 - s0 - 1) return;
