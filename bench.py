@@ -277,6 +277,10 @@ def run_ours(a):
         for h in sweep:
             for op in ops[h].locals:
                 pim_ops.plan_set_option(op.sp_info_ptr, "unit_values", 0)
+    if a.no_l2_persist:
+        for h in sweep:
+            for op in ops[h].locals:
+                pim_ops.plan_set_option(op.sp_info_ptr, "l2_persist", 0)
     x_dev = {h: graphgen.reference_features(n, h, dtype, seed=h, device=str(dev)) for h in sweep}
     # full outputs (every rank ends with all rows, ready for the next layer)
     c_full = {h: torch.empty((n, h), dtype=dtype, device=dev) for h in sweep}
@@ -582,6 +586,8 @@ def main():
                     help="N > 1: all-gather fused into the kernel epilogue (peer stores) or a separate NCCL collective")
     ap.add_argument("--no-multicast", action="store_true", help="fused gather: per-peer stores instead of multimem.st")
     ap.add_argument("--chunks", type=int, default=1, help="N > 1: sub-blocks per rank (all-gather/compute overlap)")
+    ap.add_argument("--no-l2-persist", action="store_true",
+                    help="do not put the access-policy window (persisting L2) over the dense tile")
     ap.add_argument("--general-kernel", action="store_true",
                     help="do not use the unit-value fast path (the adjacency of the benchmark is value-less => ones)")
     ap.add_argument("--workload", default="spmm", choices=["spmm", "inference"],
