@@ -2,7 +2,6 @@
 the raw C ABI with strided buffers, option handling and error reporting."""
 import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ALL_DTYPES, NP_DTYPES, features, make_args, oracle_spmm, random_adj
+from helpers import ALL_DTYPES, features, make_args, oracle_spmm, random_adj
 
 pytestmark = pytest.mark.gpu
 

@@ -3,7 +3,6 @@
 the autotuner's column tiling."""
 import types
 
-import numpy as np
 import pytest
 import torch
 
@@ -148,3 +147,25 @@ def test_autotune_picks_gpu_friendly_splits():
     assert 2.6 < autotuner.predict_ms(products, 128, 4, 1, 1) < 10.4
     st = autotuner.GraphStats.from_rowptr(torch.tensor([0, 2, 2, 5]), 4)
     assert (st.nrows, st.nnz, st.max_degree, st.empty_rows) == (3, 5, 3, 1)
+
+
+def test_bench_reference_arm_and_byte_model(tmp_path):
+    """bench.py --impl reference (the CPU arm the driver runs) on a tiny sample prints one well-formed JSON line;
+    the algorithmic-byte model matches SURVEY.md 8d."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    n, nnz = 232_965, 114_615_892
+    assert bench.alg_bytes_csr(n, n, nnz, 32) == 4 * (n + 1) + 8 * nnz + 2 * 4 * n * 32          # 977.5 MB
+    assert round(bench.alg_bytes_csr(n, n, nnz, 128) / 1e6, 1) == 1156.4
+    assert bench.alg_bytes_csr(n, n, nnz, 32, 1, "COO") == 9 * nnz + 2 * n * 32                  # INT8 COO: 1046 MB
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-rows", "512"], stdout=subprocess.PIPE, text=True, check=True)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GFLOP/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0

@@ -1,5 +1,4 @@
 """The callers around the path: quantise -> aggregate -> dequantise conv layers and the 2-layer stacks."""
-import numpy as np
 import pytest
 import torch
 
