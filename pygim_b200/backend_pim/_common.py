@@ -147,6 +147,20 @@ class SparseTensorBase:
             self.coo.append(_Coo(row.int().contiguous(), col.int().contiguous(), value.contiguous(), (n, m)))
 
     def free(self):
+        """Release the device plan (the reference leaks it: spmm_free_group is never called, spmv.py:37-41)."""
         if self.sp_info_ptr is not None:
             pim_ops.spmm_free_group(self.sp_info_ptr)
             self.sp_info_ptr = None
+
+    def __copy__(self):
+        # a shallow copy shares the index arrays but must not share (and later double-free) the plan handle
+        clone = self.__class__.__new__(self.__class__)
+        clone.__dict__.update(self.__dict__)
+        clone.sp_info_ptr = None
+        return clone
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:      # interpreter shutdown, backend already released
+            pass
