@@ -109,7 +109,8 @@ PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle);
 
 /* plan options: key in {"seg_len", "chunk_nnz", "rows_per_ticket", "unit_values", "short_rows", "host_chunks", "l2_persist"};
  * value < 0 = automatic.  unit_values = 0 forces the general kernels even when every stored value is one;
- * short_rows = 1/0 forces the high-occupancy / deep-unroll CSR instantiation; host_chunks = row chunks of the
+ * short_rows = 0/1/2 forces the deep-unroll / high-occupancy / streamed-row-ticket CSR instantiation
+ * (automatic: 2 when the mean degree is below 96, else 0); host_chunks = row chunks of the
  * host entry point (0 = no download/compute overlap); l2_persist = 1/0 forces / forbids the access-policy
  * window (persisting L2 lines) over the dense tile of a launch; automatic = on when the tile fits the carve-out. */
 PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int64_t value);

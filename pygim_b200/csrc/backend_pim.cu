@@ -384,8 +384,8 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
                                 ? (int)g->opt_rows_per_ticket
                                 : (int)std::max<long long>(1, std::min<long long>(31, 256 * std::max<long long>(p.nrows, 1) /
                                                                                      std::max<long long>(p.nnz, 1)));
-        l.short_rows = g->opt_short_rows >= 0 ? (g->opt_short_rows != 0)
-                                              : (p.nnz < 96 * std::max<long long>(p.nrows, 1));
+        l.short_rows = g->opt_short_rows >= 0 ? (int)g->opt_short_rows
+                                              : (p.nnz < 96 * std::max<long long>(p.nrows, 1) ? 2 : 0);
         l.ncols = width;
         l.ldb = ldb;
         l.ldc = ldc;

@@ -77,6 +77,16 @@ template <int E, int G> struct CsrTuneShort {
     static constexpr int D = (R > 1) ? 1 : PYGIM_SHORT_PREFETCH;
     static constexpr int MIN_BLOCKS = (E >= 8) ? PYGIM_NARROW_MINBLOCKS : ((G >= 32) ? PYGIM_CSR_MINBLOCKS : PYGIM_SHORT_MINBLOCKS);
 };
+// Streamed row tickets (short_rows == 2): 4 gathers of a run in flight, batches of 32 prefetched 2 ahead
+#ifndef PYGIM_STREAM_MINBLOCKS
+#define PYGIM_STREAM_MINBLOCKS 4
+#endif
+template <int E, int G> struct CsrTuneStream {
+    static constexpr int UNROLL = 4;
+    static constexpr int R = 1;
+    static constexpr int D = 2;
+    static constexpr int MIN_BLOCKS = PYGIM_STREAM_MINBLOCKS;
+};
 // COO carries a third index stream and the run walker: one block less per SM than CSR keeps it spill-free
 template <int E, int G> struct CooTune {
     static constexpr int UNROLL = CsrTune<E, G>::UNROLL;
@@ -86,9 +96,9 @@ template <int E, int G> struct CooTune {
 };
 
 
-template <int E, int G, bool UNIT, typename Tune>
+template <int E, int G, bool UNIT, typename Tune, bool STREAM = false>
 static cudaError_t launch_csr_t(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
-    auto kernel = csr_spmm_kernel<T, E, G, Tune::UNROLL, Tune::MIN_BLOCKS, Tune::R, Tune::D, UNIT>;
+    auto kernel = csr_spmm_kernel<T, E, G, Tune::UNROLL, Tune::MIN_BLOCKS, Tune::R, Tune::D, UNIT, STREAM>;
     static int blocks_per_sm = 0;   // per instantiation
     if (blocks_per_sm == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kCsrThreads, 0);
@@ -112,8 +122,11 @@ static cudaError_t launch_csr_t(CsrArgs<T> a, const CsrLaunch &l, int64_t *launc
 template <int E, int G, bool UNIT>
 static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t *launches) {
     // the 16-byte-word instantiations of 32/64-bit types come in two register budgets (see CsrTuneShort)
-    if constexpr (E < 8 && sizeof(T) * E >= 16 && G < 32) {
-        if (l.short_rows) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, G>>(a, l, launches);
+    if constexpr (E < 8 && sizeof(T) * E >= 16) {
+        if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTuneStream<E, G>, true>(a, l, launches);   // streamed
+        if constexpr (G < 32) {
+            if (l.short_rows) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, G>>(a, l, launches);
+        }
     }
     return launch_csr_t<E, G, UNIT, CsrTune<E, G>>(a, l, launches);
 }

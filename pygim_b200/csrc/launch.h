@@ -21,7 +21,7 @@ struct CsrLaunch {
     int *seg_count;           // [ceil(ncols/32) x n_long] zeroed arrival counters of the long rows
     int n_seg, n_long, nrows, seg_len;
     int rows_per_ticket;      // consecutive rows one work ticket covers (short-row graphs)
-    int short_rows;           // mean degree is small: prefer the high-occupancy instantiation
+    int short_rows;           // mean degree is small: 1 = high-occupancy instantiation, 2 = + streamed row tickets
     long long ncols;          // dense columns of this tile
     long long ldb, ldc, ldp;  // row strides in elements
     int accumulate;

@@ -302,9 +302,119 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
     }
 }
 
+// Write one finished row of a row ticket: combine the P interleaved partial sums (fixed xor tree) and store.
+template <typename T, int E, int G>
+__device__ __forceinline__ void csr_store_row(const CsrArgs<T> &a, typename Arith<T>::Acc (&acc)[E], int row, int vec,
+                                              bool writer) {
+    using Acc = typename Arith<T>::Acc;
+    constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
+    }
+    if (writer) {
+        const long long o = (long long)row * a.ldc + (long long)vec * E;
+        if (a.n_peers > 0) {
+            st_peers<T, E>(a.peers, a.n_peers, a.mc, o, narrow<T, E>(acc));
+        } else {
+            if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(a.C + o));
+            st_stream<T, E>(a.C + o, narrow<T, E>(acc));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+}
+
+// SHORT-ROW graphs: the rows [ja, jb) of a ticket are consecutive, so their nonzeros are ONE contiguous stream.
+// It is read in prefetched 32-entry batches that ignore row boundaries (the index-load latency of a row is hidden
+// behind the rows before it) and walked run by run - a run being the part of a row inside the batch; row ends
+// come from the ticket's rowptr entries held in the lanes (`rp`: lane l holds rowptr[first + l]).
+template <typename T, int E, int G, int UT, int D, bool UNIT>
+__device__ __forceinline__ void csr_stream_rows(const CsrArgs<T> &a, int first, int ja, int jb, int rp, int chunk) {
+    using Acc = typename Arith<T>::Acc;
+    using Shfl = typename Arith<T>::Shfl;
+    constexpr int P = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int vec = chunk * G + (lane % G);
+    const bool active = vec < a.nvec;
+    const bool writer = active && sub == 0;
+    const T *Bcol = a.B + (long long)vec * E;
+    asm volatile("" : "+l"(Bcol));
+    const int s0 = __shfl_sync(FULL, rp, ja), s1 = __shfl_sync(FULL, rp, jb);
+
+    Acc acc[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+    int cur = ja;                                        // row (relative to `first`) being accumulated
+    int boundary = __shfl_sync(FULL, rp, cur + 1);       // one past its last nonzero
+
+    int nc[D];
+    Shfl nv[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int i = s0 + d * 32 + lane;
+        nc[d] = 0;
+        nv[d] = 0;
+        if (i < s1) {
+            nc[d] = ld_stream(a.colind + i);
+            if constexpr (!UNIT) nv[d] = ld_stream(a.val + i);
+        }
+    }
+    for (int base = s0; base < s1; base += 32) {
+        const int c = nc[0];
+        const Shfl v = nv[0];
+#pragma unroll
+        for (int d = 0; d + 1 < D; ++d) { nc[d] = nc[d + 1]; nv[d] = nv[d + 1]; }
+        {
+            const int i = base + D * 32 + lane;
+            nc[D - 1] = 0;
+            nv[D - 1] = 0;
+            if (i < s1) {
+                nc[D - 1] = ld_stream(a.colind + i);
+                if constexpr (!UNIT) nv[D - 1] = ld_stream(a.val + i);
+            }
+        }
+        const int left = min(32, s1 - base);
+        int pos = 0;
+        while (pos < left) {                             // warp-uniform
+            while (boundary <= base + pos) {             // rows that ended (or are empty): write them out
+                csr_store_row<T, E, G>(a, acc, first + cur, vec, writer);
+                ++cur;
+                boundary = __shfl_sync(FULL, rp, cur + 1);
+            }
+            const int run_end = min(left, boundary - base);
+#pragma unroll 1
+            for (int s = pos; s < run_end; s += P * UT) {
+                Pack<T, E> b[UT];
+#pragma unroll
+                for (int u = 0; u < UT; ++u) {
+                    const int src = s + u * P + sub;
+                    const int cc = __shfl_sync(FULL, c, src & 31);
+                    if (active && src < run_end) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
+                }
+#pragma unroll
+                for (int u = 0; u < UT; ++u) {
+                    const int src = s + u * P + sub;
+                    Shfl vv = (Shfl)1;
+                    if constexpr (!UNIT) vv = __shfl_sync(FULL, v, src & 31);
+                    if (active && src < run_end) fma_pack<T, E>(acc, b[u], vv);
+                }
+            }
+            pos = run_end;
+        }
+    }
+    while (cur < jb) {                                   // the last row with data and any trailing empty rows
+        csr_store_row<T, E, G>(a, acc, first + cur, vec, writer);
+        ++cur;
+    }
+}
+
 // Persistent grid: gridDim.x = resident blocks of the device.  Tickets run over
 // col_chunks * (n_seg + n_row_tickets) items, column chunk outermost.
-template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D, bool UNIT>
+template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D, bool UNIT, bool STREAM = false>
 __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const __grid_constant__ CsrArgs<T> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -325,12 +435,27 @@ __global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const
         const unsigned long long nit = take_ticket();
         CsrItem nxt;
         if (nit < total) nxt = csr_load_item<T>(a, nit);
-        for (int j = 0; j < cur.count; ++j) {
-            const int start = __shfl_sync(FULL, cur.rp, j);
-            const int end = __shfl_sync(FULL, cur.rp, j + 1);
-            // rows longer than seg_len are covered by their segments + fix-up
-            if (cur.to_partial || end - start <= a.seg_len)
-                csr_process_range<T, E, G, UNROLL, R, D, UNIT>(a, start, end, cur.chunk, cur.first + j, cur.long_idx);
+        if (STREAM && !cur.to_partial) {
+            // rows longer than seg_len are covered by their segments: stream the row blocks between them
+            const int deg = __shfl_down_sync(FULL, cur.rp, 1) - cur.rp;
+            unsigned long_rows = __ballot_sync(FULL, lane < cur.count && deg > a.seg_len);
+            int ja = 0;
+            while (ja < cur.count) {
+                const unsigned rest = long_rows >> ja;
+                const int jb = rest ? ja + (__ffs(rest) - 1) : cur.count;
+                if (jb > ja)
+                    csr_stream_rows<T, E, G, (UNROLL < 4 ? UNROLL : 4), (D < 2 ? 2 : D), UNIT>(a, cur.first, ja, jb, cur.rp,
+                                                                                             cur.chunk);
+                ja = jb + 1;
+            }
+        } else {
+            for (int j = 0; j < cur.count; ++j) {
+                const int start = __shfl_sync(FULL, cur.rp, j);
+                const int end = __shfl_sync(FULL, cur.rp, j + 1);
+                // rows longer than seg_len are covered by their segments + the last-arriver merge
+                if (cur.to_partial || end - start <= a.seg_len)
+                    csr_process_range<T, E, G, UNROLL, R, D, UNIT>(a, start, end, cur.chunk, cur.first + j, cur.long_idx);
+            }
         }
         it = nit;
         cur = nxt;

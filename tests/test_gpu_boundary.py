@@ -78,7 +78,7 @@ def test_options_and_errors(gpu_backend, oracle):
     A = prepare_pim_spmm(adj, make_args(torch.float32, "CSR", 32))
     stats0 = pim_ops.plan_stats(A.sp_info_ptr)
     assert stats0["nnz"] == adj.nnz() and stats0["nrows"] == 300
-    for key, value in (("seg_len", 32), ("rows_per_ticket", 7), ("short_rows", 1), ("short_rows", 0),
+    for key, value in (("seg_len", 32), ("rows_per_ticket", 7), ("short_rows", 1), ("short_rows", 2), ("short_rows", 0),
                        ("unit_values", 0), ("host_chunks", 3), ("l2_persist", 1), ("l2_persist", 0), ("seg_len", -1)):
         pim_ops.plan_set_option(A.sp_info_ptr, key, value)
         assert torch.equal(A.mul(x), want), (key, value)

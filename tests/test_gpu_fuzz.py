@@ -39,6 +39,8 @@ def test_random_configuration(gpu_backend, oracle, seed):
         pim_ops.plan_set_option(A.sp_info_ptr, "rows_per_ticket", int(rng.integers(1, 32)))
     if rng.random() < 0.3:
         pim_ops.plan_set_option(A.sp_info_ptr, "chunk_nnz", int(rng.choice([32, 64, 256])))
+    if rng.random() < 0.6:
+        pim_ops.plan_set_option(A.sp_info_ptr, "short_rows", int(rng.integers(0, 3)))   # 2 = streamed row tickets
     if rng.random() < 0.3:
         pim_ops.plan_set_option(A.sp_info_ptr, "host_chunks", int(rng.integers(1, 4)))
     info = (seed, dtype, fmt, n, m, hidden, density, sp, ds, with_values, on_gpu)

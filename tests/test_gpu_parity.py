@@ -151,3 +151,39 @@ def test_unit_value_fast_path_equals_general_kernel(gpu_backend, oracle, fmt):
         A2 = prepare_pim_spmm(adj2, make_args(dtype, fmt, 48))
         assert torch.equal(A2.mul(x), oracle_spmm(oracle, adj2, x, dtype)), dtype
         A2.free()
+
+
+@pytest.mark.parametrize("rows_per_ticket", [1, 5, 31])
+def test_streamed_row_tickets(gpu_backend, oracle, rows_per_ticket):
+    """short_rows = 2: the rows of a ticket are read as one contiguous nonzero stream (products-/citation-like
+    graphs).  Covers empty rows at every position, rows longer than seg_len inside a ticket (handled by segments),
+    accumulation over sparse parts, column tiles and the unit-value path."""
+    from pygim_b200 import graphgen
+    from pygim_b200.backend_pim import pim_ops
+    from pygim_b200.backend_pim.spmm import prepare_pim_spmm
+    adj = graphgen.synthetic_adj("products", scale=0.002, seed=4)           # ~4.9 K rows, mean degree ~25, long rows
+    n = adj.size(0)
+    rowptr, col, _ = adj.csr()
+    for dtype, hidden, sp, ds in ((torch.float32, 32, 1, 1), (torch.float32, 64, 2, 2), (torch.int32, 16, 1, 1),
+                                  (torch.float64, 32, 1, 1), (torch.float32, 128, 1, 1)):
+        x = features(n, hidden, dtype, seed=3)
+        want = torch.from_numpy(oracle.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy()))
+        A = prepare_pim_spmm(adj.to("cuda"), make_args(dtype, "CSR", hidden, sp_parts=sp, ds_parts=ds))
+        pim_ops.plan_set_option(A.sp_info_ptr, "short_rows", 2)
+        pim_ops.plan_set_option(A.sp_info_ptr, "rows_per_ticket", rows_per_ticket)
+        for seg_len in (-1, 64):
+            pim_ops.plan_set_option(A.sp_info_ptr, "seg_len", seg_len)
+            for unit in (-1, 0):
+                pim_ops.plan_set_option(A.sp_info_ptr, "unit_values", unit)
+                got = A.mul(x.cuda())
+                torch.cuda.synchronize()
+                assert torch.equal(got.cpu(), want), (dtype, hidden, sp, ds, seg_len, unit)
+        A.free()
+    # empty rows everywhere + explicit values
+    adj2 = random_adj(500, 400, 0.01, seed=7, value_dtype=torch.float32, empty_rows=tuple(range(0, 500, 3)))
+    x2 = features(400, 32, torch.float32, seed=1)
+    A2 = prepare_pim_spmm(adj2, make_args(torch.float32, "CSR", 32))
+    pim_ops.plan_set_option(A2.sp_info_ptr, "short_rows", 2)
+    pim_ops.plan_set_option(A2.sp_info_ptr, "rows_per_ticket", rows_per_ticket)
+    assert torch.equal(A2.mul(x2), oracle_spmm(oracle, adj2, x2, torch.float32))
+    A2.free()
