@@ -38,4 +38,8 @@ for DT in INT8 INT16 INT32 INT64 FLT32 DBL64; do
   gcc $COMMON $DEF_SPMV -D$DT=1 -I"$V" -shared -o "$OUT/libref_spmv_$DT.so" \
       "$V/spmv_mul_coo.c" "$V/support/partition.c" "$V/support/timer.c" "$STUBS/dpu_stubs.c"
 done
+# the row-balanced partitioners are compiled out of the default build (BLNC_ROW=0): a seventh library with them
+D="$REF/spmm_default"
+gcc $COMMON -DINT32=1 -DBLNC_ROW=1 -DBLNC_NNZ=1 -DBLNC_NNZ_RGRN=1 -DBLNC_TSKLT_ROW=1 -DBLNC_TSKLT_NNZ=1 \
+    -DBLNC_TSKLT_NNZ_RGRN=1 -I"$D" -shared -o "$OUT/libref_partition.so" "$D/support/partition.c"
 echo "built $(ls "$OUT" | wc -l) reference host-oracle libraries in $OUT"

@@ -40,7 +40,7 @@ def build(native: bool = False, force: bool = False) -> str:
             os.path.getmtime(target) < os.path.getmtime(os.path.join(_HERE, "spmm_oracle.c")):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir(os.environ.get("PYGIM_REFERENCE_ROOT", "/root/reference")):
-        if force or not os.path.isdir(os.path.join(_HERE, "_ref")) or len(os.listdir(os.path.join(_HERE, "_ref"))) < 18:
+        if force or not os.path.isdir(os.path.join(_HERE, "_ref")) or len(os.listdir(os.path.join(_HERE, "_ref"))) < 19:
             subprocess.check_call([os.path.join(_HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
     return target
 
@@ -253,3 +253,15 @@ def ref_add_2d(A: np.ndarray, B: np.ndarray, off_x: int, off_y: int) -> np.ndarr
                                        C.c_uint32(off_x), C.c_uint32(off_y), C.c_uint32(B.shape[0]),
                                        C.c_uint32(B.shape[1]))
     return A
+
+
+def ref_partition_rows(rowptr, nparts: int, policy: str = "row") -> np.ndarray:
+    """The reference's partition_by_row_csr / partition_by_nnz_csr (spmm_default/support/partition.c:14-44, 51-99)."""
+    rowptr = _i32(rowptr)
+    nrows = rowptr.shape[0] - 1
+    A = _RefCSR(nrows, 0, int(rowptr[-1]), rowptr.ctypes.data, None, None, rowptr.shape[0], 0, 0)
+    out = np.zeros(nparts + 2, dtype=np.uint32)
+    l = C.CDLL(os.path.join(_HERE, "_ref", "libref_partition.so"))
+    f = l.partition_by_row_csr if policy == "row" else l.partition_by_nnz_csr
+    f(C.byref(A), _p(out), C.c_int(nparts))
+    return out[: nparts + 1].astype(np.int64)

@@ -76,3 +76,28 @@ def test_rowpar_matches_scipy_and_torch(oracle):
                                       (80, 70))
         want = torch.sparse.mm(coo, torch.from_numpy(x)).numpy()      # wraps modulo 2^n for ints
         assert np.array_equal(oracle.spmm_coo(row, col, val, x, 80), want)
+
+
+def test_row_partitioners_against_the_reference(ref):
+    """pygim_partition_rows_even == the reference's partition_by_row_csr; pygim_partition_rows_by_nnz (nearest row
+    boundary to every k/n quantile) balances at least as well as the reference's greedy partition_by_nnz_csr overall
+    and never much worse on a single case (support/partition.c:14-44, 51-99)."""
+    import torch
+    from pygim_b200.backend_pim import pim_ops
+    rng = np.random.default_rng(3)
+    total_ours = total_theirs = 0
+    for trial in range(30):
+        nrows = int(rng.integers(1, 400))
+        nparts = int(rng.integers(1, 12))
+        deg = (rng.pareto(1.2, nrows) * 5).astype(np.int64)
+        rowptr = np.zeros(nrows + 1, dtype=np.int32)
+        np.cumsum(deg, out=rowptr[1:])
+        assert list(ref.ref_partition_rows(rowptr, nparts, "row")) == pim_ops.partition_rows_even(nrows, nparts)
+        ours = pim_ops.partition_rows_by_nnz(torch.from_numpy(rowptr), nparts)
+        theirs = ref.ref_partition_rows(rowptr, nparts, "nnz")
+        assert ours[0] == 0 and ours[-1] == nrows and ours == sorted(ours)
+        load = lambda sp: max(int(rowptr[sp[i + 1]] - rowptr[sp[i]]) for i in range(nparts))
+        assert load(ours) <= 1.1 * load(theirs), (trial, ours, list(theirs))
+        total_ours += load(ours)
+        total_theirs += load(theirs)
+    assert total_ours <= total_theirs
