@@ -163,9 +163,10 @@ PYGIM_API int pygim_last_launches(pygim_handle_t handle, int64_t *out);
 
 /* ---------------------------------------------------------------- partitioners (host, no GPU needed)
  * GPU-level analogue of partition_by_nnz_csr (support/partition.c:51-99): cut [0, nrows) into
- * nparts contiguous row ranges of near-equal nnz.  Unlike the reference's greedy sweep (which resets
- * its running count at every cut and merges the leftovers into the last part) cut p is the row
- * boundary whose prefix nnz is nearest to p*nnz/nparts.  split_out has nparts+1 entries. */
+ * nparts contiguous row ranges of near-equal nnz.  Where the reference sweeps greedily against nnz/n
+ * (and merges the leftovers into the last part), this returns the contiguous partition whose HEAVIEST part is as
+ * light as possible (binary search on the bound + greedy sweep), so it is never worse balanced than the
+ * reference's.  split_out has nparts+1 entries; parts that are not needed are empty. */
 PYGIM_API int pygim_partition_rows_by_nnz(const int32_t *rowptr, int64_t nrows, int nparts, int64_t *split_out);
 /* partition_by_row_csr (support/partition.c:14-44): nrows/nparts rows each, first nrows%nparts get +1 */
 PYGIM_API int pygim_partition_rows_even(int64_t nrows, int nparts, int64_t *split_out);

@@ -893,19 +893,35 @@ PYGIM_API int pygim_last_launches(pygim_handle_t handle, int64_t *out) {
 
 PYGIM_API int pygim_partition_rows_by_nnz(const int32_t *rowptr, int64_t nrows, int nparts, int64_t *split_out) {
     if (!rowptr || !split_out || nparts <= 0 || nrows < 0) return fail(PYGIM_ERR_INVALID, "bad partition arguments");
-    const long long nnz = (unsigned)rowptr[nrows];
-    split_out[0] = 0;
-    long long r = 0;
-    for (int p = 1; p < nparts; ++p) {
-        const long long target = (nnz * p + nparts - 1) / nparts;
-        // row boundary whose prefix nnz is nearest to the target (never before the previous cut)
-        const int32_t *it = std::lower_bound(rowptr + r, rowptr + nrows + 1, target,
-                                             [](int32_t a, long long t) { return (long long)(unsigned)a < t; });
-        long long hi = std::min<long long>(it - rowptr, nrows);
-        if (hi > r && target - (long long)(unsigned)rowptr[hi - 1] <= (long long)(unsigned)rowptr[hi] - target) --hi;
-        r = hi;
-        split_out[p] = r;
+    auto at = [&](long long r) { return (long long)(unsigned)rowptr[r]; };
+    const long long nnz = at(nrows);
+    // Contiguous partition with the smallest possible heaviest part: binary search on the bound T, feasibility by
+    // a greedy sweep that jumps with upper_bound over the prefix sums (rowptr itself).
+    auto sweep = [&](long long T, int64_t *out) -> int {      // number of parts needed with every part <= T
+        long long r = 0;
+        int parts = 0;
+        while (r < nrows) {
+            const long long limit = at(r) + T;
+            const int32_t *it = std::upper_bound(rowptr + r, rowptr + nrows + 1, limit,
+                                                 [](long long t, int32_t a) { return t < (long long)(unsigned)a; });
+            long long next = (it - rowptr) - 1;                // last boundary with prefix <= limit
+            if (next <= r) next = r + 1;                       // a single row heavier than T (only when T < max row)
+            if (out && parts + 1 <= nparts) out[parts + 1] = next;
+            ++parts;
+            r = next;
+        }
+        return parts;
+    };
+    long long lo = 0, hi = std::max<long long>(nnz, 1);
+    for (long long r = 0; r < nrows; ++r) lo = std::max(lo, at(r + 1) - at(r));
+    lo = std::max(lo, (nnz + nparts - 1) / nparts);
+    while (lo < hi) {
+        const long long mid = lo + (hi - lo) / 2;
+        if (sweep(mid, nullptr) <= nparts) hi = mid; else lo = mid + 1;
     }
+    split_out[0] = 0;
+    for (int p = 1; p <= nparts; ++p) split_out[p] = nrows;    // parts the sweep does not need stay empty
+    sweep(lo, split_out);
     split_out[nparts] = nrows;
     return PYGIM_OK;
 }
