@@ -298,7 +298,6 @@ template <typename L> static cudaError_t dispatch_coo(int dtype, const L &l, int
     }
 }
 
-// C[:, col0:col0+w] (+)= A_i * B_tile[rows_i, :]  for one (sparse part, dense tile)
 // Access-policy window over the dense tile a launch gathers from: its lines are kept as "persisting" in the L2
 // carve-out while the A stream (read once, evict-first) and the C stores pass through.  `touched` = bytes of the
 // window the kernel really reads (a column tile touches only its own columns of every row).
@@ -323,6 +322,7 @@ struct PeerDst {        // destinations of the fused all-gather (empty => plain 
     char *mc = nullptr;
 };
 
+// C[:, col0:col0+w] (+)= A_i * B_tile[rows_i, :]  for one (sparse part, dense tile[, row range of the plan])
 static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char *C, long long ldc, long long width,
                     bool accumulate, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0,
                     CsrPlan *plan = nullptr) {
