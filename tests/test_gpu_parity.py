@@ -187,3 +187,22 @@ def test_streamed_row_tickets(gpu_backend, oracle, rows_per_ticket):
     pim_ops.plan_set_option(A2.sp_info_ptr, "rows_per_ticket", rows_per_ticket)
     assert torch.equal(A2.mul(x2), oracle_spmm(oracle, adj2, x2, torch.float32))
     A2.free()
+
+
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+def test_duplicate_edges_are_summed(gpu_backend, oracle, fmt):
+    """Duplicate (row, col) entries: the COO front-end coalesces them (spmm.py:40-42 `.coalesce()`), the CSR
+    front-end keeps them as separate nonzeros - either way they add up, in the value dtype (int8 wraps)."""
+    from pygim_b200.sparse_tensor import SparseTensor
+    rng = np.random.default_rng(5)
+    n, m, nnz = 150, 120, 4000
+    row = torch.from_numpy(rng.integers(0, n, nnz))
+    col = torch.from_numpy(rng.integers(0, m, nnz))          # ~20 % of the pairs repeat
+    for dtype in (torch.int8, torch.float32, torch.int64):
+        val = torch.from_numpy(rng.integers(-100, 100, nnz)).to(dtype)
+        adj = SparseTensor(row=row, col=col, value=val, sparse_sizes=(n, m))
+        x = features(m, 24, dtype, seed=2)
+        out = _run("spmm", adj, make_args(dtype, fmt, 24), x)
+        r, c, v = adj.coo()
+        want = torch.from_numpy(oracle.spmm_coo(r.numpy(), c.numpy(), v.numpy(), x.numpy(), n))
+        assert torch.equal(out, want), dtype
