@@ -4,24 +4,29 @@
 // multigroup copies).  Where a DPU tasklet walks a contiguous row block and issues one MRAM read
 // of dense_size*byte_dt bytes per nonzero (:108-126), here:
 //
-//  * the grid is PERSISTENT (resident warps only); every warp pulls work items from a global
-//    (self-resetting, CUDA-graph friendly) ticket counter, so no warp idles while another still owns a long row (the reference's
-//    second-level balancing, partition_tsklt_by_nnz_csr, support/partition.c:186-229, made dynamic);
-//  * a work item is a whole row, or - for rows longer than seg_len - one seg_len-bounded segment
-//    of a row; segment items come first in ticket order, longest first;
-//  * the warp reads 32 column indices and 32 values per coalesced evict-first load, TWO batches
-//    ahead of the one being consumed, and hands them round with shuffles: the HBM latency of the
-//    index stream is off the critical path of the gathers;
-//  * the next item's ticket and row bounds are fetched before the current item is processed;
+//  * the grid is PERSISTENT (resident warps only); every warp pulls work items from a global,
+//    self-resetting (CUDA-graph friendly) ticket counter, so no warp idles while another still owns
+//    a long row (the reference's second-level balancing, partition_tsklt_by_nnz_csr,
+//    support/partition.c:186-229, made dynamic);
+//  * a work item is a group of 1..31 consecutive rows (about 256 nonzeros), or - for rows longer
+//    than seg_len - one seg_len-bounded segment of a row; segments come first, longest first;
+//  * the warp reads 32*R column indices and values per coalesced evict-first load, D batches ahead
+//    of the one being consumed, and hands them round with shuffles: the HBM latency of the index
+//    stream is off the critical path of the gathers.  The next ticket and its rowptr entries are
+//    fetched before the current item is processed;
 //  * a dense row of H elements is covered by G lanes, each moving one 16-byte word (float4,
 //    16 x int8, ...), so P = 32/G nonzeros are gathered by every load instruction and UNROLL
-//    independent gathers per lane are in flight before the first FMA consumes one;
+//    independent gathers per lane are in flight before the first FMA consumes one.  The gather
+//    address is one IMAD.WIDE.U32 (32-bit byte stride, base held in registers);
 //  * the P partial sums are combined by an xor-shuffle tree in a fixed order (deterministic), and
 //    the row is written once with a streaming store - no host merge (memcpy_2D / memadd_2D,
-//    spmm_mul_csr.c:41-86) remains.
-//
-// Segment items write to a partial buffer; the last segment of a row to finish adds the row's partials in
-// segment order and writes the row (no second kernel, no floating-point atomics).
+//    spmm_mul_csr.c:41-86) remains.  With peers set, the row goes to every GPU instead (fused
+//    all-gather over NVLink);
+//  * a segment publishes its partial sum; the last segment of a row to arrive adds the row's
+//    partials in slot order and writes the row (no second kernel, no floating-point atomics);
+//  * short-row graphs take csr_stream_rows: the consecutive rows of a ticket are ONE contiguous
+//    nonzero stream, read in prefetched batches that ignore row boundaries and walked run by run;
+//  * UNIT: when the plan found every stored value equal to one, the value stream is not read.
 #pragma once
 #include "vec.cuh"
 
