@@ -37,14 +37,14 @@ class DeviceModel:
     launch_us: float = 4.0
     # a row is a dependent chain (index load -> gather -> shuffle tree -> store) that one warp walks alone:
     # short-row graphs are bound by rows x row_latency / resident warps (measured on products-shape, 16-byte rows)
-    row_latency_us: float = 1.9
-    resident_warps_per_sm: int = 24
+    row_latency_us: float = 1.3          # with streamed row tickets (1.9 without)
+    resident_warps_per_sm: int = 32
     # gather rate out of L2 (TB/s of gathered payload) vs bytes per gathered row
-    l2_gather_tbs: Dict[int, float] = field(default_factory=lambda: {16: 3.0, 32: 6.0, 64: 12.0, 128: 16.0,
-                                                                     256: 18.5, 512: 18.0})
+    l2_gather_tbs: Dict[int, float] = field(default_factory=lambda: {16: 3.2, 32: 6.5, 64: 13.0, 128: 19.0,
+                                                                     256: 19.8, 512: 19.5})
     # fraction of hbm_gbs reached when the rows are gathered from HBM (B >> L2)
-    hbm_gather_eff: Dict[int, float] = field(default_factory=lambda: {16: 0.08, 32: 0.15, 64: 0.35, 128: 0.61,
-                                                                      256: 0.81, 512: 0.93})
+    hbm_gather_eff: Dict[int, float] = field(default_factory=lambda: {16: 0.10, 32: 0.20, 64: 0.55, 128: 0.85,
+                                                                      256: 0.97, 512: 1.00})
 
     @classmethod
     def from_environment(cls, info: Optional[dict] = None) -> "DeviceModel":
