@@ -195,6 +195,276 @@ def run_reference(a):
 
 
 # ====================================================================================== GPU arm
+class SweepWorkload:
+    """One graph shape, row-sharded over the ranks, with one plan per hidden size of the sweep."""
+
+    def __init__(self, a, shape, dev, rank, world, clustered=False, reorder=None, sweep=None, tag=""):
+        import torch
+        from pygim_b200 import graphgen
+        from pygim_b200.backend_pim import pim_ops
+        from pygim_b200.backend_pim.spmm import TORCH_TYPES, SparseTensorCOO
+        from pygim_b200.sharded import ShardedSpMM, shard_rows
+        from pygim_b200.sparse_tensor import SparseTensor
+        self.a, self.shape, self.dev, self.rank, self.world, self.tag = a, shape, dev, rank, world, tag
+        self.clustered, self.reorder = clustered, reorder
+        self.dtype = TORCH_TYPES[a.dtype]
+        self.esize = torch.empty((), dtype=self.dtype).element_size()
+        self.n, self.nnz, self.max_deg = graphgen.SHAPES[shape]
+        self.sweep = list(sweep or a.hidden or HIDDEN_SWEEP)
+        self.info = pim_ops.device_info()
+        n, nnz, max_deg = self.n, self.nnz, self.max_deg
+        # ---- this rank's row shard (nnz-balanced, the GPU-level partition_by_nnz_csr)
+        self.deg = graphgen.degree_sequence(n, nnz, max_deg, n, seed=0)
+        full_rowptr = torch.zeros(n + 1, dtype=torch.int64)
+        torch.cumsum(self.deg, 0, out=full_rowptr[1:])
+        self.splits = pim_ops.partition_rows_by_nnz(full_rowptr, world) if world > 1 else [0, n]
+        self.r0, self.r1 = self.splits[rank], self.splits[rank + 1]
+        self._full = None
+        if clustered:
+            # the block-model generator draws rows in one sequence: every rank generates the graph and keeps its block
+            rowptr, col = graphgen.clustered_csr(n, nnz, max_deg, seed=0, device=str(dev), deg=self.deg)
+            full = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(n, n), is_sorted=True)
+            self._full = full
+            adj = full if world == 1 else shard_rows(full, self.r0, self.r1)
+        else:
+            rowptr, col = graphgen.synthetic_csr(n, nnz, max_deg, seed=0, device=str(dev), rows=(self.r0, self.r1),
+                                                 deg=self.deg)
+            adj = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(self.r1 - self.r0, n), is_sorted=True)
+        del rowptr, col
+        self.adj_plain = adj                       # rows in natural order (parity checks read it)
+        self.shard_nnz = int(adj.nnz())
+        self.reorder_stats = None
+        perm = None
+        if reorder:
+            from pygim_b200 import reorder as R
+            t0 = time.perf_counter()
+            adj, perm, self.reorder_stats = R.reorder_rows(adj, reorder)
+            torch.cuda.synchronize()
+            self.reorder_stats["seconds"] = time.perf_counter() - t0
+        self.ds_parts = {h: (a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, self.info, self.esize))
+                         for h in self.sweep}
+        base = SparseTensorCOO(adj, dtype=self.dtype, format=a.format)
+        base.row_perm = perm
+        base.build_csr() if a.format == "CSR" else base.build_coo()
+        self.plans = {}
+        for h in self.sweep:     # one set of int32 CSR/COO arrays shared by the plans (one plan per hidden size)
+            A = copy.copy(base)
+            A.sp_info_ptr = None
+            A.to_pim_group(h, self.ds_parts[h])
+            self.plans[h] = A
+
+        def args_for(h):
+            ns = make_args(h, self.dtype, a.format)
+            ns.ds_parts = self.ds_parts[h]
+            return ns
+
+        self.gather = a.gather
+        self.ops = {h: ShardedSpMM(None, args_for(h), splits=self.splits, local_adj=adj,
+                                   make_local=lambda _adj, _args, _h=h: self.plans[_h], chunks=1,
+                                   fused=(world > 1 and a.gather == "fused"), use_multicast=not a.no_multicast,
+                                   sync=a.sync) for h in self.sweep}
+        for h in self.sweep:
+            hdl = self.plans[h].sp_info_ptr
+            if a.general_kernel:     # force the weighted kernels although the adjacency is value-less (all ones)
+                pim_ops.plan_set_option(hdl, "unit_values", 0)
+            if a.short_rows is not None:
+                pim_ops.plan_set_option(hdl, "short_rows", a.short_rows)
+            if a.no_l2_persist:
+                pim_ops.plan_set_option(hdl, "l2_persist", 0)
+            for kv in a.opt or []:
+                k, v = kv.split("=")
+                pim_ops.plan_set_option(hdl, k, int(v))
+        self.x_dev = {h: graphgen.reference_features(n, h, self.dtype, seed=h, device=str(dev)) for h in self.sweep}
+        self.c_full = {h: torch.empty((n, h), dtype=self.dtype, device=dev) for h in self.sweep}
+        self.c_last = dict(self.c_full)
+
+    def probe_fused(self):
+        """The fused path needs NVLink peer mappings (symmetric memory); if this box cannot provide them every rank
+        falls back to the NCCL all-gather together and the JSON line says so."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1 or self.gather != "fused":
+            return
+        ok = torch.ones(1, device=self.dev)
+        try:
+            self.ops[self.sweep[0]].mul(self.x_dev[self.sweep[0]])
+            torch.cuda.synchronize()
+        except Exception as exc:      # noqa: BLE001
+            ok.zero_()
+            if self.rank == 0:
+                print("bench.py: fused all-gather unavailable (%s); using NCCL" % str(exc)[:200], file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            self.gather = "nccl"
+            for h in self.sweep:
+                self.ops[h].fused = False
+
+    def step(self, record=None, exchange=True):
+        for i, h in enumerate(self.sweep):
+            if record is not None:
+                record[i][0].record()
+            if not exchange:
+                self.ops[h].mul(self.x_dev[h], out=self.c_full[h], gather=False)     # this rank's row block only
+            elif self.world > 1 and self.gather == "fused":
+                self.c_last[h] = self.ops[h].mul(self.x_dev[h])   # rows land in every peer's symmetric buffer
+            else:
+                self.ops[h].mul(self.x_dev[h], out=self.c_full[h])   # N > 1: SpMM of the row block + NCCL all-gather
+                self.c_last[h] = self.c_full[h]
+            if record is not None:
+                record[i][1].record()
+
+    def sync(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(self, steps, warmup, exchange=True):
+        """(ms per step [max over ranks], per-hidden ms [max over ranks]) with CUDA events on the launching stream."""
+        import torch
+        import torch.distributed as dist
+        for _ in range(warmup):
+            self.step(exchange=exchange)
+        self.sync()
+        ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in self.sweep]
+              for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.sync()
+        t0.record()
+        for k in range(steps):
+            self.step(ev[k], exchange=exchange)
+        t1.record()
+        self.sync()
+        ms = t0.elapsed_time(t1) / steps
+        per_h = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(steps)) / steps for i in range(len(self.sweep))]
+        if self.world > 1:
+            t = torch.tensor([ms] + per_h, dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, per_h = float(t[0]), [float(v) for v in t[1:]]
+        return ms, per_h
+
+    def flops_step(self):
+        return sum(2.0 * self.nnz * h for h in self.sweep)
+
+    def block_rows(self, j):
+        """(rowptr, col) of rank j's row block on this device - regenerated from the seed for foreign blocks."""
+        from pygim_b200 import graphgen
+        from pygim_b200.sharded import shard_rows
+        if j == self.rank:
+            rp, cl, _ = self.adj_plain.csr()
+            return rp, cl
+        if self._full is not None:
+            sh = shard_rows(self._full, self.splits[j], self.splits[j + 1])
+            rp, cl, _ = sh.csr()
+            return rp, cl
+        return graphgen.synthetic_csr(self.n, self.nnz, self.max_deg, seed=0, device=str(self.dev),
+                                      rows=(self.splits[j], self.splits[j + 1]), deg=self.deg)
+
+    def parity_all_ranks(self, O, results, x_host, rows_per_block=256):
+        """EVERY rank checks sampled rows of EVERY rank's block of the gathered result - including each block's
+        longest (segmented) row - against the oracle; the verdicts are AND-reduced.  This is the reference's
+        exact-equality self-check (spmm_multigroup/mul_csr_multigroup.c:550-620) applied to what was just timed."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        ok, checked = True, 0
+        for j in range(self.world):
+            rp, cl = self.block_rows(j)
+            nb = rp.numel() - 1
+            if nb == 0:
+                continue
+            deg = rp[1:] - rp[:-1]
+            g = torch.Generator().manual_seed(1000 + j)
+            pick = torch.randperm(nb, generator=g)[: max(0, min(rows_per_block, nb) - 1)]
+            pick = torch.unique(torch.cat([pick, torch.argmax(deg).cpu().view(1)])).to(rp.device)
+            cnt = deg[pick]
+            src = torch.repeat_interleave(rp[:-1][pick], cnt) + \
+                (torch.arange(int(cnt.sum()), device=rp.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt))
+            sub_col = cl[src].cpu().numpy().astype("int32")
+            sub_rp = np.zeros(pick.numel() + 1, dtype="int32")
+            np.cumsum(cnt.cpu().numpy(), out=sub_rp[1:])
+            rows_glob = (pick + self.splits[j]).to(self.dev)
+            for h in self.sweep:
+                want = O.spmm_csr_rowpar(sub_rp, sub_col, None, x_host[h].numpy(), nthreads=O.max_threads())
+                got = results[h][rows_glob].cpu().numpy()
+                ok = ok and bool(np.array_equal(want, got))
+            checked += int(pick.numel())
+            del rp, cl
+        if self.world > 1:
+            t = torch.tensor([1.0 if ok else 0.0], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(float(t) == 1.0)
+        return ok, checked
+
+    def free(self):
+        import torch
+        for h in self.sweep:
+            self.ops[h]._symm.clear()
+            self.plans[h].free()
+        self.x_dev.clear(); self.c_full.clear(); self.c_last.clear()
+        self._full = None
+        self.adj_plain = None
+        torch.cuda.empty_cache()
+
+
+def per_hidden_table(w, per_h_ms, peak):
+    out = []
+    for i, h in enumerate(w.sweep):
+        # per-GPU algorithmic bytes of this rank's SpMM (shard of A and C, all of B), A counted once
+        b = alg_bytes_csr(w.r1 - w.r0, w.n, w.shard_nnz, h, w.esize, w.a.format)
+        out.append({"hidden": h, "kernel_ms": per_h_ms[i], "gflops": 2.0 * w.shard_nnz * h / per_h_ms[i] / 1e6,
+                    "alg_gbs": b / per_h_ms[i] / 1e6, "frac_hbm": b / per_h_ms[i] / 1e6 / peak,
+                    "gather_gbs": float(w.esize) * w.shard_nnz * h / per_h_ms[i] / 1e6,
+                    "launches": w.ds_parts[h], "tile_cols": h // w.ds_parts[h]})
+    return out
+
+
+def selftest_multi(a, dev, rank, world):
+    """Whole-matrix parity of every multi-GPU mode on a small Reddit-like graph (what tests/test_gpu_multi.py checks,
+    run here because the driver's GPU-test box has one GPU): every rank compares the FULL gathered result."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from pygim_b200 import graphgen
+    from pygim_b200.sharded import ColumnShardedSpMM, ShardedSpMM
+    O.build()
+    adj = graphgen.synthetic_adj("reddit", scale=0.01, seed=5)
+    n = adj.size(0)
+    rowptr, col, _ = adj.csr()
+    ok, modes = True, []
+    for dtype, hidden in ((torch.float32, 64), (torch.int32, 32)):
+        x = graphgen.reference_features(n, hidden, dtype, seed=1)
+        args = make_args(hidden, dtype, "CSR")
+        want = O.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy())
+        for kw in (dict(chunks=1), dict(chunks=3), dict(fused=True, sync="flags"),
+                   dict(fused=True, sync="flags", use_multicast=False), dict(fused=True, sync="barrier")):
+            try:
+                op = ShardedSpMM(adj.to(str(dev)), args, **kw)
+                for _ in range(5):
+                    out = op.mul(x.to(dev))
+                torch.cuda.synchronize()
+                good = bool(np.array_equal(out.cpu().numpy(), want))
+                op.free()
+            except Exception as exc:       # noqa: BLE001
+                good = False
+                print("selftest-multi rank %d: %s failed: %s" % (rank, kw, str(exc)[:300]), file=sys.stderr)
+            ok = ok and good
+            if dtype == torch.float32:
+                modes.append("+".join("%s=%s" % kv for kv in kw.items()))
+    x = graphgen.reference_features(n, 48, torch.float32, seed=2)
+    cop = ColumnShardedSpMM(adj.to(str(dev)), make_args(48, torch.float32, "CSR"))
+    out = cop.mul(x.to(dev))
+    torch.cuda.synchronize()
+    ok = ok and bool(np.array_equal(out.cpu().numpy(), O.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy())))
+    cop.free()
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(float(t) == 1.0), modes + ["column-sharded"]
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -209,179 +479,138 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from pygim_b200 import graphgen
     from pygim_b200.backend_pim import pim_ops
-    from pygim_b200.backend_pim.spmm import SparseTensorCOO
-    from pygim_b200.sparse_tensor import SparseTensor
-
-    from pygim_b200.backend_pim.spmm import TORCH_TYPES
-    dtype = TORCH_TYPES[a.dtype]
-    esize = torch.empty((), dtype=dtype).element_size()
-    n, nnz, max_deg = graphgen.SHAPES[a.shape]
-    sweep = a.hidden if a.hidden else HIDDEN_SWEEP
     pim_ops.dpu_init_ranks(1)
-    info = pim_ops.device_info()
+    steps, warmup = a.steps, max(a.warmup, 3)
 
-    # ---- this rank's row shard (nnz-balanced, the GPU-level partition_by_nnz_csr)
-    deg = graphgen.degree_sequence(n, nnz, max_deg, n, seed=0)
-    full_rowptr = torch.zeros(n + 1, dtype=torch.int64)
-    torch.cumsum(deg, 0, out=full_rowptr[1:])
-    splits = pim_ops.partition_rows_by_nnz(full_rowptr, world) if world > 1 else [0, n]
-    r0, r1 = splits[rank], splits[rank + 1]
-    rowptr, col = graphgen.synthetic_csr(n, nnz, max_deg, seed=0, device=str(dev), rows=(r0, r1), deg=deg)
-    shard_nnz = int(col.numel())
-    adj = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(r1 - r0, n), is_sorted=True)
-    del rowptr, col
-    from pygim_b200.sharded import ShardedSpMM
-    ds_parts = {h: (a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, info, esize)) for h in sweep}
+    selftest = None
+    if world > 1 and not a.no_selftest:
+        selftest = selftest_multi(a, dev, rank, world)
 
-    def args_for(h):
-        ns = make_args(h, dtype, a.format)
-        ns.ds_parts = ds_parts[h]
-        return ns
-
-    if world == 1:
-        # one set of int32 CSR/COO arrays shared by the four plans (one plan per hidden size)
-        base = SparseTensorCOO(adj, dtype=dtype, format=a.format)
-        base.build_csr() if a.format == "CSR" else base.build_coo()
-        plans = {}
-        for h in sweep:
-            A = copy.copy(base)
-            A.sp_info_ptr = None
-            A.to_pim_group(h, ds_parts[h])
-            plans[h] = A
-        ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj,
-                              make_local=lambda _adj, _args, _h=h: plans[_h]) for h in sweep}
-    else:
-        ops = {h: ShardedSpMM(None, args_for(h), splits=splits, local_adj=adj, chunks=a.chunks,
-                              fused=(a.gather == "fused"), use_multicast=not a.no_multicast) for h in sweep}
-        plans = {h: ops[h].locals[0] for h in sweep}
-        if a.gather == "fused":
-            # the fused path needs NVLink peer mappings (symmetric memory); if this box cannot provide them, every
-            # rank falls back to the NCCL all-gather together and the JSON line says so
-            ok = torch.ones(1, device=dev)
-            try:
-                probe = torch.zeros((n, sweep[0]), dtype=dtype, device=dev)
-                ops[sweep[0]].mul(probe)
-                torch.cuda.synchronize()
-            except Exception as exc:      # noqa: BLE001
-                ok.zero_()
-                if rank == 0:
-                    print("bench.py: fused all-gather unavailable (%s); using NCCL" % str(exc)[:200], file=sys.stderr)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if float(ok) == 0.0:
-                a.gather = "nccl"
-                for h in sweep:
-                    ops[h].fused = False
-    if a.general_kernel:     # force the weighted kernels although the adjacency is value-less (all ones)
-        for h in sweep:
-            for op in ops[h].locals:
-                pim_ops.plan_set_option(op.sp_info_ptr, "unit_values", 0)
-    if a.short_rows is not None:
-        for h in sweep:
-            for op in ops[h].locals:
-                pim_ops.plan_set_option(op.sp_info_ptr, "short_rows", a.short_rows)
-    if a.no_l2_persist:
-        for h in sweep:
-            for op in ops[h].locals:
-                pim_ops.plan_set_option(op.sp_info_ptr, "l2_persist", 0)
-    x_dev = {h: graphgen.reference_features(n, h, dtype, seed=h, device=str(dev)) for h in sweep}
-    # full outputs (every rank ends with all rows, ready for the next layer)
-    c_full = {h: torch.empty((n, h), dtype=dtype, device=dev) for h in sweep}
-
-    c_last = dict(c_full)
-
-    def step_device(record=None):
-        for i, h in enumerate(sweep):
-            if record is not None:
-                record[i][0].record()
-            if world > 1 and a.gather == "fused":
-                c_last[h] = ops[h].mul(x_dev[h])       # rows land in every peer's symmetric buffer (no collective)
-            else:
-                ops[h].mul(x_dev[h], out=c_full[h])    # N > 1: SpMM of the row block(s) + NCCL all-gather
-            if record is not None:
-                record[i][1].record()
-
-    def sync():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
+    w = SweepWorkload(a, a.shape, dev, rank, world, clustered=a.clustered, reorder=a.reorder)
+    w.probe_fused()
+    sweep, n, nnz, esize = w.sweep, w.n, w.nnz, w.esize
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
-    for _ in range(max(a.warmup, 3)):
-        step_device()
-    sync()
+    for _ in range(warmup):
+        w.step()
+    w.sync()
     sampler.mark()               # report only samples taken from here (timed region + e2e region) on
-    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in sweep]
-          for _ in range(a.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    t_begin.record()
-    for k in range(a.steps):
-        step_device(ev[k])
-    t_end.record()
-    sync()
-    elapsed_ms = t_begin.elapsed_time(t_end)
-    launches_per_step = sum(pim_ops.last_launches(op.sp_info_ptr) for h in sweep for op in ops[h].locals)
-    per_h_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(a.steps)) / a.steps
-                for i in range(len(sweep))]
+    ms_step, per_h_ms = w.timed(steps, 0)
+    launches_per_step = sum(pim_ops.last_launches(w.plans[h].sp_info_ptr) for h in sweep)
     if world > 1:
-        t = torch.tensor([elapsed_ms] + per_h_ms, dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, per_h_ms = float(t[0]), [float(v) for v in t[1:]]
-    flops_step = sum(2.0 * nnz * h for h in sweep)
-    value = flops_step * a.steps / (elapsed_ms * 1e-3) / 1e9
-
-    # ---- e2e: same step through the public API with pinned HOST operands (H2D + D2H inside the timing)
-    x_host = {h: x_dev[h].cpu().pin_memory() for h in sweep}
-    c_host = {h: torch.empty((r1 - r0, h), dtype=dtype).pin_memory() for h in sweep}
-
-    def step_host():
-        for h in sweep:
-            if world == 1:
-                plans[h].mul(x_host[h], out=c_host[h])
-            else:   # each rank's row block(s) through the host entry point; no collective on host results
-                blk = ops[h]
-                for k, op in enumerate(blk.locals):
-                    op.mul(x_host[h], out=c_host[h][blk.sub[k]:blk.sub[k + 1]])
-
-    e2e_steps = max(3, min(a.steps, 10)) if not a.no_e2e else 1
-    for _ in range(2 if not a.no_e2e else 0):
-        step_host()
-    sync()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    sync()
-    e2e_s = time.perf_counter() - t0
+        launches_per_step += len(sweep) if (w.gather == "fused" and a.sync == "flags") else 0     # the one-warp waits
+    value = w.flops_step() / (ms_step * 1e-3) / 1e9
+    # the same step WITHOUT the exchange (report both)
+    no_exchange = None
     if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-    e2e_value = flops_step * e2e_steps / e2e_s / 1e9
+        ms_nx, per_h_nx = w.timed(steps, 2, exchange=False)
+        no_exchange = {"value": w.flops_step() / (ms_nx * 1e-3) / 1e9, "ms_per_step": ms_nx, "per_hidden_ms": per_h_nx}
+        w.step()                 # c_last holds gathered results again (parity below)
+        w.sync()
+
+    # ---- e2e: the same step through the public API with pinned HOST operands (H2D + D2H inside the timing)
+    x_host = {h: w.x_dev[h].cpu().pin_memory() for h in sweep}
+    e2e = None
+    if not a.no_e2e:
+        if world == 1:
+            c_host = {h: torch.empty((n, h), dtype=w.dtype).pin_memory() for h in sweep}
+            handles = [w.plans[h].sp_info_ptr for h in sweep]
+
+            def step_host():
+                if a.e2e_mode == "pipelined":     # one software pipeline over the sweep's four calls
+                    pim_ops.spmm_run_dense_many(handles, [x_host[h] for h in sweep], [c_host[h] for h in sweep])
+                else:                             # four independent synchronous calls (host entry point)
+                    for h in sweep:
+                        w.plans[h].mul(x_host[h], out=c_host[h])
+            h2d = sum(n * h * esize for h in sweep)
+            d2h = h2d
+        else:
+            # every rank uploads only ITS 1/N row block of B over PCIe; the blocks are all-gathered over NVLink into
+            # the full operand, the SpMM runs from device memory and only this rank's rows of C go back to the host
+            blk = [(n * r) // world for r in range(world + 1)]
+            b0, b1 = blk[rank], blk[rank + 1]
+            pad = max(blk[r + 1] - blk[r] for r in range(world))
+            xb_host = {h: x_host[h][b0:b1].clone().pin_memory() for h in sweep}
+            xg = {h: torch.empty((world * pad, h), dtype=w.dtype, device=dev) for h in sweep}
+            x_full = {h: torch.empty((n, h), dtype=w.dtype, device=dev) for h in sweep}
+            c_host = {h: torch.empty((w.r1 - w.r0, h), dtype=w.dtype).pin_memory() for h in sweep}
+            c_loc = {h: torch.empty((n, h), dtype=w.dtype, device=dev) for h in sweep}
+
+            def step_host():
+                for h in sweep:
+                    mine = xg[h][rank * pad: rank * pad + (b1 - b0)]
+                    mine.copy_(xb_host[h], non_blocking=True)
+                    dist.all_gather_into_tensor(xg[h], xg[h][rank * pad:(rank + 1) * pad])
+                    for r in range(world):
+                        x_full[h][blk[r]:blk[r + 1]].copy_(xg[h][r * pad: r * pad + blk[r + 1] - blk[r]])
+                    w.ops[h].mul(x_full[h], out=c_loc[h], gather=False)
+                    c_host[h].copy_(c_loc[h][w.r0:w.r1], non_blocking=True)
+                torch.cuda.synchronize()
+            h2d = sum((b1 - b0) * h * esize for h in sweep)
+            d2h = sum((w.r1 - w.r0) * h * esize for h in sweep)
+        e2e_steps = max(3, min(steps, 10))
+        for _ in range(2):
+            step_host()
+        w.sync()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        w.sync()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            e2e_s, h2d, d2h = float(tm[0]), int(t[1]), int(t[2])
+        e2e = {"value": w.flops_step() * e2e_steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+               "mode": (a.e2e_mode if world == 1 else "row block of B per rank over PCIe + NVLink all-gather, "
+                        "local rows of C back (bytes are totals over ranks)")}
+        if world == 1 and a.e2e_mode != "pipelined":
+            e2e["phases_ms"] = {str(h): pim_ops.last_timers(w.plans[h].sp_info_ptr) for h in sweep}
     clocks = sampler.stop() if rank == 0 else None
-    h2d = sum(n * h * esize for h in sweep)
-    d2h = sum((r1 - r0) * h * esize for h in sweep)
-    timers = {h: pim_ops.last_timers(plans[h].sp_info_ptr) for h in sweep}
 
-    # ---- parity spot check of what was just timed (rank 0, first rows, against the oracle)
-    parity = None
-    if rank == 0 and not a.no_check:
+    # ---- parity of what was just timed: every rank, sampled rows of every rank's block, against the oracle
+    parity, parity_rows, parity_e2e = None, 0, None
+    if not a.no_check:
         import numpy as np
         from oracle import oracle as O
         O.build()
-        rows_chk = min(256, r1 - r0)
-        rp, cl, _ = adj.csr()
-        rp_h = rp[: rows_chk + 1].cpu().numpy().astype("int32")
-        cl_h = cl[: int(rp_h[-1])].cpu().numpy().astype("int32")
-        parity = True
-        for h in sweep:
-            want = O.spmm_csr_rowpar(rp_h, cl_h, None, x_host[h].numpy(), nthreads=O.max_threads())
-            parity = parity and bool(np.array_equal(want, c_last[h][r0:r0 + rows_chk].cpu().numpy())) \
-                and bool(np.array_equal(want, c_host[h][:rows_chk].numpy()))
+        parity, parity_rows = w.parity_all_ranks(O, w.c_last, x_host)
+        if e2e is not None:      # the host-path results: this rank's first rows
+            rows_chk = min(256, w.r1 - w.r0)
+            rp, cl, _ = w.adj_plain.csr()
+            rp_h = rp[: rows_chk + 1].cpu().numpy().astype("int32")
+            cl_h = cl[: int(rp_h[-1])].cpu().numpy().astype("int32")
+            parity_e2e = True
+            for h in sweep:
+                want = O.spmm_csr_rowpar(rp_h, cl_h, None, x_host[h].numpy(), nthreads=O.max_threads())
+                off = w.r0 if world == 1 else 0
+                parity_e2e = parity_e2e and bool(np.array_equal(want, c_host[h][off:off + rows_chk].numpy()))
+            if world > 1:
+                t = torch.tensor([1.0 if parity_e2e else 0.0], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                parity_e2e = bool(float(t) == 1.0)
+
+    peak, peak_kind = measured_peaks()
+    per_hidden = per_hidden_table(w, per_h_ms, peak)
+    shard_nnz, r0, r1, ds_parts = w.shard_nnz, w.r0, w.r1, w.ds_parts
+    adj_for_cpu = w.adj_plain if (world == 1 and not a.no_cpu) else None
+    if world > 1:
+        x_full = xg = c_loc = None
+    if adj_for_cpu is None:
+        w.free()
+
+    # ---- sub-records (same process, same box): the clustered graph with prepare-time reordering, products-shape
+    clustered_rec = products_rec = None
+    if a.shape == "reddit" and not a.clustered and a.dtype == "FLT32" and a.format == "CSR" and not a.hidden:
+        if world == 1 and not a.no_clustered:
+            clustered_rec = run_sub_workload(a, "reddit", dev, rank, world, peak, clustered=True)
+        if not a.no_products:
+            products_rec = run_sub_workload(a, "products", dev, rank, world, peak, clustered=False)
 
     if rank != 0:
         if world > 1:
@@ -389,47 +618,40 @@ def run_ours(a):
         return
 
     # ---- roofline of the dominant kernel (largest share of the step)
-    peak, peak_kind = measured_peaks()
-    per_hidden = []
-    for i, h in enumerate(sweep):
-        # per-GPU algorithmic bytes of this rank's SpMM (shard of A and C, all of B), A counted once
-        b = alg_bytes_csr(r1 - r0, n, shard_nnz, h, esize, a.format)
-        per_hidden.append({"hidden": h, "kernel_ms": per_h_ms[i], "gflops": 2.0 * shard_nnz * h / per_h_ms[i] / 1e6,
-                           "alg_gbs": b / per_h_ms[i] / 1e6, "frac_hbm": b / per_h_ms[i] / 1e6 / peak,
-                           "gather_gbs": float(esize) * shard_nnz * h / per_h_ms[i] / 1e6,
-                           "launches": ds_parts[h], "tile_cols": h // ds_parts[h]})
     # The dominant KERNEL is the template instantiation with the largest share of the step.  An instantiation
     # is fixed by the dense tile a launch handles (G = lanes per tile row), so hidden sizes that run as
     # several column tiles (H = 128 -> two 64-column launches) are launches of the SAME kernel as H = 64.
     # Per launch the algorithmic bytes are A + that tile of B + that tile of C (SURVEY.md 8d with H = tile).
     by_kernel = {}
     for i, h in enumerate(sweep):
-        w = h // ds_parts[h]
-        k = by_kernel.setdefault(w, {"ms": 0.0, "launches": 0, "bytes": 0.0, "hidden": []})
+        wd = h // ds_parts[h]
+        k = by_kernel.setdefault(wd, {"ms": 0.0, "launches": 0, "bytes": 0.0, "hidden": []})
         k["ms"] += per_h_ms[i]
         k["launches"] += ds_parts[h]
-        k["bytes"] += ds_parts[h] * alg_bytes_csr(r1 - r0, n, shard_nnz, w, esize, a.format)
+        k["bytes"] += ds_parts[h] * alg_bytes_csr(r1 - r0, n, shard_nnz, wd, esize, a.format)
         k["hidden"].append(h)
-    dom_w = max(by_kernel, key=lambda w: by_kernel[w]["ms"])
+    dom_w = max(by_kernel, key=lambda wd: by_kernel[wd]["ms"])
     dk = by_kernel[dom_w]
     lanes = max(1, min(32, dom_w * esize // 16))
     roof = {"bound": "hbm",
-            "kernel": "%s_spmm_kernel<%s, G=%d> (%d-column tiles; hidden %s)"
-                      % (a.format.lower(), a.dtype, lanes, dom_w, "/".join(map(str, dk["hidden"]))),
+            "kernel": "csr_spmm_kernel<%s, G=%d> (%d-column tiles; hidden %s)%s"
+                      % (a.dtype, lanes, dom_w, "/".join(map(str, dk["hidden"])),
+                         " over the row pointer derived from the sorted COO stream" if a.format == "COO" else ""),
             "achieved": dk["bytes"] / dk["ms"] / 1e6, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
             "frac": dk["bytes"] / dk["ms"] / 1e6 / peak, "traffic": None,
             "alg_bytes_per_launch": dk["bytes"] / dk["launches"], "launches_per_step": dk["launches"],
             "avg_launch_ms": dk["ms"] / dk["launches"], "share_of_step": dk["ms"] / sum(per_h_ms),
             "sweep_achieved": sum(alg_bytes_csr(r1 - r0, n, shard_nnz, h, esize, a.format) for h in sweep)
             / sum(per_h_ms) / 1e6,
-            "note": "Reddit-shape is L2-gather bound (s*nnz*H bytes leave L2 per launch), see DESIGN.md 4.3"}
+            "note": "uniformly random Reddit-shape is bound by L2 -> SM gather traffic (s*nnz*H bytes leave L2 per "
+                    "launch), see DESIGN.md 4.3; the `clustered` sub-record is the same shape with community structure"}
     # secondary bound: the measured ceiling of random row gathers (tools/l2_gather_probe)
     try:
         with open(os.path.join(ROOT, "profiles", "gather_ceiling.json")) as f:
             ceil = json.load(f)
         row_bytes = dom_w * esize
         key = str(min((64, 128, 256, 512), key=lambda b: abs(b - row_bytes)))
-        resident = n * row_bytes <= 0.46 * info["l2_bytes"]
+        resident = n * row_bytes <= 0.46 * w.info["l2_bytes"]
         peak_g = ceil["l2_resident_tbs" if resident else "hbm_served_tbs"][key]
         ach_g = float(esize) * shard_nnz * sum(h for h in dk["hidden"]) / dk["ms"] / 1e9
         roof["gather"] = {"bound": "l2-gather" if resident else "hbm-gather", "achieved_tbs": ach_g,
@@ -439,23 +661,26 @@ def run_ours(a):
     except Exception:
         pass
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_path) and (a.shape, a.dtype, a.format, world) == ("reddit", "FLT32", "CSR", 1):
+    if os.path.exists(traffic_path) and (a.shape, a.dtype, a.format, world, a.clustered) == ("reddit", "FLT32", "CSR", 1, False):
         try:
             with open(traffic_path) as f:
-                roof["traffic"] = json.load(f).get("tile_%d" % dom_w)
+                tj = json.load(f)
+            roof["traffic"] = tj.get("tile_%d" % dom_w)
+            roof["traffic_source"] = tj.get("source", "profiles/traffic.json (one ncu --set full capture of this kernel; "
+                                                      "not measured in this run)")
         except Exception:
             pass
 
     # ---- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
     cpu = None
-    if world == 1 and not a.no_cpu:
+    if adj_for_cpu is not None:
         from oracle import oracle as O
         O.build()
         native = O.build_native()
         clib = O.lib(native) if native else O.lib()
         threads = O.max_threads()
         sample_rows = min(a.cpu_sample_rows or n, r1 - r0)         # default: the whole workload
-        rp, cl, _ = adj.csr()
+        rp, cl, _ = adj_for_cpu.csr()
         rp_h = rp[: sample_rows + 1].cpu().numpy().astype("int32")
         cl_h = cl[: int(rp_h[-1])].cpu().numpy().astype("int32")
         xs = {h: x_host[h].numpy() for h in sweep}
@@ -463,35 +688,90 @@ def run_ours(a):
         cpu = {"value": fl / secs / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "rows [0,%d) of the same graph (%d nnz), hidden sweep %s, best of 3 passes (%.2f s each)"
                          % (sample_rows, int(rp_h[-1]), sweep, secs), "native_build": bool(native)}
+        w.free()
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"FLT32": "f32", "DBL64": "f64", "INT8": "i8", "INT16": "i16", "INT32": "i32", "INT64": "i64"}[a.dtype],
         "data": "synthetic",
-        "config": {"workload": "%s-shape %s %s SpMM, hidden sweep %s" % (a.shape, a.dtype, a.format,
-                                                                         "/".join(map(str, sweep))),
+        "config": {"workload": "%s-shape%s %s %s SpMM, hidden sweep %s" % (a.shape, " (block-model communities)" if a.clustered else "",
+                                                                            a.dtype, a.format, "/".join(map(str, sweep))),
                    "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": a.format, "sp_parts": 1,
                    "values": "all ones (value-less adjacency); " + ("general weighted kernel forced" if a.general_kernel
                              else "unit-value fast path: value stream not read, results bit-identical"),
                    "ds_parts": {str(h): ds_parts[h] for h in sweep},
+                   "reorder": a.reorder or "none",
                    "sharding": ("rows by nnz over %d GPUs, B replicated, all-gather of C %s, inside the timing"
-                                % (world, "fused into the kernel epilogue (NVLink peer stores)" if a.gather == "fused"
-                                   else "by NCCL (%d sub-blocks per rank)" % a.chunks))
+                                % (world, ("fused into the kernel epilogue (NVLink %s stores, %s)"
+                                           % ("per-peer" if a.no_multicast else "multimem",
+                                              "in-kernel arrival flags, no barrier" if a.sync == "flags" else "one barrier per call"))
+                                   if w.gather == "fused" else "by NCCL"))
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (A = %.0f MB streams through a %.0f MB L2 every launch)"
-                         % ((8.0 * nnz) / 1e6, info["l2_bytes"] / 1e6)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-                "phases_ms": {str(h): timers[h] for h in sweep}},
-        "gpu_launches": launches_per_step * a.steps,
+                         % ((8.0 * nnz) / 1e6, w.info["l2_bytes"] / 1e6)},
+        "e2e": e2e, "gpu_launches": launches_per_step * steps,
         "roofline": roof, "per_hidden": per_hidden, "cpu_baseline": cpu, "clocks": clocks,
-        "parity_spot_check": parity,
+        "parity_all_ranks": parity, "parity_rows_checked_per_rank": parity_rows, "parity_e2e": parity_e2e,
+        "no_exchange": no_exchange, "selftest_multi": None if selftest is None else {"ok": selftest[0], "modes": selftest[1]},
+        "clustered": clustered_rec, "products": products_rec, "reorder_stats": w.reorder_stats,
         "lib": os.path.relpath(__import__("pygim_b200._lib", fromlist=["x"]).loaded_path() or "", ROOT),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sub_workload(a, shape, dev, rank, world, peak, clustered):
+    """A second workload in the same process (same box, same clocks): the block-model Reddit-shape graph with
+    prepare-time reordering (N = 1), or products-shape (BASELINE.json configs[4]) with and without the exchange and -
+    at N > 1 - rank 0 alone on the whole graph as the single-GPU reference of the speed-up."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    steps, warmup = max(5, min(a.steps, 10)), 3
+    rec = {}
+    variants = [("reordered", "cluster"), ("natural_order", None)] if clustered else [("sharded", None)]
+    for name, reorder in variants:
+        w = SweepWorkload(a, shape, dev, rank, world, clustered=clustered, reorder=reorder)
+        if clustered and reorder:
+            from pygim_b200.backend_pim import pim_ops
+            for h in w.sweep:
+                for k, v in (("cta_threads", a.clustered_cta), ("max_g", a.clustered_max_g)):
+                    if v:
+                        pim_ops.plan_set_option(w.plans[h].sp_info_ptr, k, v)
+        w.probe_fused()
+        ms, per_h = w.timed(steps, warmup)
+        r = {"value": w.flops_step() / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms,
+             "per_hidden": per_hidden_table(w, per_h, peak), "reorder_stats": w.reorder_stats}
+        if world > 1:
+            ms_nx, per_nx = w.timed(steps, 2, exchange=False)
+            r["no_exchange"] = {"value": w.flops_step() / (ms_nx * 1e-3) / 1e9, "ms_per_step": ms_nx, "per_hidden_ms": per_nx}
+            # NVLink bytes every GPU must RECEIVE per step with a replicated result, against the measured 770 GB/s
+            ingress = sum((w.n - (w.r1 - w.r0)) * h * w.esize for h in w.sweep)
+            r["exchange_floor_ms"] = ingress / 770e9 * 1e3
+            w.step()
+            w.sync()
+        if not a.no_check:
+            O.build()
+            x_host = {h: w.x_dev[h].cpu() for h in w.sweep}
+            r["parity_all_ranks"], r["parity_rows_checked_per_rank"] = w.parity_all_ranks(O, w.c_last, x_host)
+        rec[name] = r
+        w.free()
+    if not clustered and world > 1:
+        # single-GPU reference of the speed-up: rank 0 alone on the whole graph, the other ranks wait
+        if rank == 0:
+            w1 = SweepWorkload(a, shape, dev, 0, 1)
+            ms1, _ = w1.timed(steps, warmup)
+            rec["n1_same_box"] = {"value": w1.flops_step() / (ms1 * 1e-3) / 1e9, "ms_per_step": ms1}
+            rec["speedup_with_exchange"] = rec["sharded"]["value"] / rec["n1_same_box"]["value"]
+            rec["speedup_without_exchange"] = rec["sharded"]["no_exchange"]["value"] / rec["n1_same_box"]["value"]
+            w1.free()
+        dist.barrier()
+    rec["config"] = {"workload": "%s-shape%s FLT32 CSR SpMM, hidden sweep %s" % (
+        shape, " with block-model communities (1024 nodes, 70 %% of a row's edges inside)" if clustered else "",
+        "/".join(map(str, HIDDEN_SWEEP))), "n_gpus": world}
+    return rec
 
 
 # ====================================================================================== inference workload
@@ -596,6 +876,19 @@ def main():
                     help="do not put the access-policy window (persisting L2) over the dense tile")
     ap.add_argument("--general-kernel", action="store_true",
                     help="do not use the unit-value fast path (the adjacency of the benchmark is value-less => ones)")
+    ap.add_argument("--sync", default="flags", choices=["flags", "barrier"],
+                    help="fused gather: in-kernel arrival flags (no barrier) or one symmetric-memory barrier per call")
+    ap.add_argument("--clustered", action="store_true",
+                    help="headline graph with block-model communities (same N, nnz, degrees) instead of uniform columns")
+    ap.add_argument("--reorder", default=None, choices=["cluster", "degree"], help="prepare-time row reordering")
+    ap.add_argument("--opt", action="append", help="plan option key=value (pygim_plan_set_option), repeatable")
+    ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "per-call"],
+                    help="N = 1 host-operand step: one pipeline over the sweep (spmm_run_dense_many) or four host calls")
+    ap.add_argument("--no-selftest", action="store_true", help="N > 1: skip the whole-matrix multi-GPU self-test")
+    ap.add_argument("--no-clustered", action="store_true", help="skip the clustered-graph sub-record (N = 1)")
+    ap.add_argument("--no-products", action="store_true", help="skip the products-shape sub-record")
+    ap.add_argument("--clustered-cta", type=int, default=0, help="cta_threads of the reordered clustered plans")
+    ap.add_argument("--clustered-max-g", type=int, default=0, help="max_g of the reordered clustered plans")
     ap.add_argument("--workload", default="spmm", choices=["spmm", "inference"],
                     help="spmm = the headline hidden sweep; inference = 2-layer GCN/GIN/SAGE end to end (configs[3])")
     a = ap.parse_args()

@@ -107,18 +107,39 @@ PYGIM_API int pygim_spmm_to_device_group(int format, int dtype, int n_sp, const 
 /* spmm_free_group (spmm_default/pytorch_api.cpp:198-201; never called by the reference's Python) */
 PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle);
 
-/* plan options: key in {"seg_len", "chunk_nnz", "rows_per_ticket", "unit_values", "short_rows", "host_chunks", "l2_persist"};
- * value < 0 = automatic.  unit_values = 0 forces the general kernels even when every stored value is one;
- * short_rows = 0/1/2 forces the deep-unroll / high-occupancy / streamed-row-ticket CSR instantiation
- * (automatic: 2 when the mean degree is below 96, else 0); host_chunks = row chunks of the
- * host entry point (0 = no download/compute overlap); l2_persist = 1/0 forces / forbids the access-policy
- * window (persisting L2 lines) over the dense tile of a launch; automatic = on when the tile fits the carve-out. */
+/* plan options (the knobs the retargeted autotuner turns, utils/autotuner.py); value < 0 = automatic:
+ *   seg_len          rows with more nonzeros are cut into segments of at most this many
+ *   item_nnz         short rows are grouped into work items of about this many nonzeros (default 256) ...
+ *   rows_per_ticket  ... and at most this many rows (1..31)
+ *   super_nnz        nonzeros per superticket - the unit an SM's warps drain together (default nnz / (16 SMs))
+ *   cta_threads      threads per block (256 default; 1024 = ONE block per SM, every warp of the SM on the same
+ *                    superticket: use with a locality-preserving row order so gathered rows are L1 hits)
+ *   max_g            lanes per dense row are capped at this power of two; wider rows run as column chunks of one
+ *                    launch (8 = 128-byte chunks, the L1 line)
+ *   short_rows       0/1/2 = deep-unroll / high-occupancy / streamed-row-item CSR instantiation (automatic: 2 when
+ *                    the mean degree is below 96, else 0)
+ *   unit_values      0 forces the general kernels even when every stored value is one
+ *   coo_native       1 runs a sorted COO plan through the COO (segmented reduction) kernel instead of the CSR
+ *                    kernels over the derived row pointer
+ *   chunk_nnz        COO kernel: nonzeros per work item
+ *   host_chunks      row chunks of the host entry point (0 = no download/compute overlap)
+ *   l2_persist       1/0 forces / forbids the access-policy window (persisting L2 lines) over the dense tile of a
+ *                    launch; automatic = on when the tile fits the carve-out */
 PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int64_t value);
 
 /* Graph statistics the retargeted autotuner consumes (the role of pim_ops.prepare_tune_csr,
  * utils/autotuner.py:295-302,351): out[0..7] = nrows, ncols, nnz, max row nnz, number of long
  * rows (cut into segments), number of segments, seg_len, empty rows - for sparse part `part`. */
 PYGIM_API int pygim_plan_stats(pygim_handle_t handle, int part, int64_t *out8);
+/* out[0..5] = work items, supertickets, 1 if a COO plan runs through the CSR kernels (row-major sorted stream),
+ * 1 if the COO stream is sorted, 1 if a row map is set, 1 if every stored value is one - for sparse part `part`. */
+PYGIM_API int pygim_plan_layout(pygim_handle_t handle, int part, int64_t *out6);
+
+/* Row reordering (the role ClusterData plays at spmm_test.py:57-65): the plan's sparse parts were
+ * built from a ROW-PERMUTED adjacency (rows that share neighbours next to each other, so the SM that processes them
+ * re-uses the gathered feature rows out of its L1); plan row r is row row_map[r] of the result, and the kernels
+ * scatter on store - callers see the original row order.  n must equal the plan's row count; NULL clears the map. */
+PYGIM_API int pygim_plan_set_row_map(pygim_handle_t handle, const int32_t *row_map, int64_t n, int mem);
 
 /* ---------------------------------------------------------------- run ("run_group")
  * Replaces spmm_csr_run_group / spmm_coo_run_group / spmv_coo_run_group
@@ -151,6 +172,44 @@ PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ld
  * The caller provides the cross-rank barriers before (peers done reading) and after (rows visible) the call. */
 PYGIM_API int pygim_spmm_device_peers(pygim_handle_t handle, const void *B, int64_t ldb, void *const *C_peers,
                                       int n_peers, void *C_multicast, int64_t ldc, int64_t row_offset, void *stream);
+
+/* Everything a conv layer does around the aggregation, fused into the row store of the SpMM
+ * (models/pyg_gcn_conv.py:130-137, pyg_gin_conv.py:80-101, models/quantize.py:40-42), plus the multi-GPU exchange.
+ * All fields optional (zero = off):
+ *   scale            device scalar: the result is FLOAT32, (float)sum * scale[0] - symmetric_dequantize
+ *   residual         device float32 [rows x h_size], row stride ld_residual: result += residual_coeff * residual
+ *                    (GIN's (1 + eps) * x_r); one multiply, one multiply, one add, never contracted
+ *   C_peers / n_peers / C_multicast / row_offset   as pygim_spmm_device_peers (C is then ignored)
+ *   row_peer_mask    device, one byte per plan row: bit p set = peer p needs this row (halo exchange); NULL = all
+ *   flag_peers / my_rank / epoch   in-kernel arrival signal: when this rank's last row has been stored the kernel
+ *                    writes `epoch` to flag_peers[p][my_rank] of every peer p (release, system scope); consumers
+ *                    wait with pygim_wait_flags instead of a cross-rank barrier per call
+ * ldc is in elements of the RESULT type (float32 when scale or residual is set).  Needs sp_parts == 1. */
+typedef struct {
+    const float *scale;
+    const float *residual;
+    int64_t ld_residual;
+    float residual_coeff;
+    void *const *C_peers;
+    int n_peers;
+    void *C_multicast;
+    int64_t row_offset;
+    const uint8_t *row_peer_mask;
+    int32_t *const *flag_peers;
+    int my_rank;
+    int32_t epoch;
+} pygim_epilogue_t;
+PYGIM_API int pygim_spmm_device_ex(pygim_handle_t handle, const void *B, int64_t ldb, void *C, int64_t ldc,
+                                   const pygim_epilogue_t *epi, void *stream);
+/* enqueue a wait on `stream` until flags[0..n) have all reached `epoch` (n <= 32) */
+PYGIM_API int pygim_wait_flags(const int32_t *flags, int n, int32_t epoch, void *stream);
+
+/* symmetric_quantize (models/quantize.py:20-38) as two kernels: scale[0] = 2 * max|x| / 2^k (k = 5 / 10 / 20 for
+ * INT8 / INT16 / INT32 and FLT32), xq = round_half_even(x / scale) stored as `dtype`.  x is float32
+ * [rows x cols] with row stride ldx, xq has row stride ldq; scale is a device float.  Bit-identical to the torch
+ * expression (IEEE division, rintf).  INT64 / DBL64 are rejected (the reference's else-branch quantises to float). */
+PYGIM_API int pygim_quantize(const float *x, int64_t rows, int64_t cols, int64_t ldx, int dtype, void *xq, int64_t ldq,
+                             float *scale, void *stream);
 
 /* The five phase timers the reference prints as [DATA]load_sparse_time / load_dense_time /
  * kernel_time / retrieve_result_time / alignment_time (spmm_mul_csr.c:563-580), in ms, for the

@@ -23,7 +23,16 @@ SYMBOLS = [
     "pygim_device_info", "pygim_spmm_to_device_group", "pygim_spmm_free_group", "pygim_plan_set_option",
     "pygim_plan_stats", "pygim_spmm_run_group_host", "pygim_spmm_run_group_device", "pygim_spmm_device", "pygim_spmm_device_peers",
     "pygim_last_timers", "pygim_last_launches", "pygim_partition_rows_by_nnz", "pygim_partition_rows_even",
+    "pygim_plan_layout", "pygim_plan_set_row_map", "pygim_spmm_device_ex", "pygim_wait_flags", "pygim_quantize",
 ]
+
+
+class Epilogue(C.Structure):
+    """pygim_epilogue_t (include/pygim_b200.h)."""
+    _fields_ = [("scale", C.c_void_p), ("residual", C.c_void_p), ("ld_residual", C.c_int64),
+                ("residual_coeff", C.c_float), ("C_peers", C.POINTER(C.c_void_p)), ("n_peers", C.c_int),
+                ("C_multicast", C.c_void_p), ("row_offset", C.c_int64), ("row_peer_mask", C.c_void_p),
+                ("flag_peers", C.POINTER(C.c_void_p)), ("my_rank", C.c_int), ("epoch", C.c_int32)]
 
 _lib: Optional[C.CDLL] = None
 _lib_path: Optional[str] = None
@@ -56,6 +65,11 @@ def _declare(lib: C.CDLL) -> None:
     lib.pygim_last_launches.argtypes = [C.c_uint64, P(i64)]
     lib.pygim_partition_rows_by_nnz.argtypes = [vp, i64, ci, P(i64)]
     lib.pygim_partition_rows_even.argtypes = [i64, ci, P(i64)]
+    lib.pygim_plan_layout.argtypes = [C.c_uint64, ci, P(i64)]
+    lib.pygim_plan_set_row_map.argtypes = [C.c_uint64, vp, i64, ci]
+    lib.pygim_spmm_device_ex.argtypes = [C.c_uint64, vp, i64, vp, i64, P(Epilogue), vp]
+    lib.pygim_wait_flags.argtypes = [vp, ci, i32, vp]
+    lib.pygim_quantize.argtypes = [vp, i64, i64, i64, ci, vp, i64, vp, vp]
     for name in SYMBOLS:
         if name != "pygim_last_error":
             getattr(lib, name).restype = ci

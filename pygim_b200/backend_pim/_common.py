@@ -111,6 +111,17 @@ class SparseTensorBase:
         self.hidden_size = 0
         self.nparts = 1
         self.format = format
+        # row reordering (pygim_b200/reorder.py): `raw` then holds the row-permuted adjacency and row_perm[r] is the
+        # original row of its row r; the plan scatters on store, so mul() returns rows in the original order
+        self.row_perm = None
+        self.plan_options = {}
+
+    def _plan_created(self):
+        """Attach what belongs to the plan besides the sparse arrays: the row map and the tuned options."""
+        if self.row_perm is not None:
+            pim_ops.plan_set_row_map(self.sp_info_ptr, self.row_perm)
+        for key, value in self.plan_options.items():
+            pim_ops.plan_set_option(self.sp_info_ptr, key, value)
 
     # -- column split of the adjacency (sparse parts; partial products are summed)
     def col_split(self, nparts=4):
@@ -145,6 +156,24 @@ class SparseTensorBase:
                 n, m = n + pad, m + pad
             row, col, value = coalesce(row, col, edge_values(item, self.dtype), m)
             self.coo.append(_Coo(row.int().contiguous(), col.int().contiguous(), value.contiguous(), (n, m)))
+
+    _FUSED_DTYPES = (torch.int8, torch.int16, torch.int32, torch.float32)
+
+    def mul_fused(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, residual_coeff: float = 1.0):
+        """symmetric_quantize -> A @ x_q -> symmetric_dequantize (+ residual_coeff * residual) as the conv layers
+        do around `mul` (models/pyg_gcn_conv.py:130-137, pyg_gin_conv.py:80-101), with the elementwise passes fused
+        into the kernels: one absmax + one quantise kernel produce x_q, the SpMM's row store de-quantises and adds
+        the residual.  Bit-identical to the unfused torch expression.  Returns None when the fusion does not apply
+        (host operand, several sparse parts, 64-bit dtypes) - the caller then composes it from `mul`."""
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and len(self.parts) == 1 and
+                self.dtype in self._FUSED_DTYPES and self.sp_info_ptr is not None):
+            return None
+        if self.format == "COO" and not pim_ops.plan_layout(self.sp_info_ptr)["coo_runs_as_csr"]:
+            return None
+        assert self.hidden_size == x.size(1)
+        scale, x_q = pim_ops.quantize(x, self.dtype)
+        return pim_ops.spmm_run_dense_ex(self.sp_info_ptr, x_q, scale=scale, residual=residual,
+                                         residual_coeff=residual_coeff)
 
     def free(self):
         """Release the device plan (the reference leaks it: spmm_free_group is never called, spmv.py:37-41)."""

@@ -61,6 +61,7 @@ class SparseTensorCOO(SparseTensorBase):
             [p.crow_indices() for p in self.csr], [p.col_indices() for p in self.csr],
             [p.values() for p in self.csr], [p.size(0) for p in self.csr], [p.size(1) for p in self.csr],
             self.dense_ncols, hidden_size)
+        self._plan_created()
 
     def mul(self, B: torch.Tensor, out=None):
         assert self.hidden_size == B.size(1)

@@ -45,6 +45,8 @@ class _GroupMeta:
     grande_cols: Optional[List[List[int]]] = None
     part_ncols: Optional[List[int]] = None
     variant: str = "spmm"   # spmm | grande | spmv
+    # the column tiles the LIBRARY plans (spmv: one `groups`-wide tile although the op is handed `groups` vectors)
+    lib_dense_cols: Optional[List[int]] = None
 
 
 _GROUPS: Dict[int, _GroupMeta] = {}
@@ -75,9 +77,11 @@ def dpu_init_dpus(nr_dpus: int) -> None:
 
 
 def dpu_release() -> None:
-    """spmm_default/pytorch_api.cpp:162-164.  Plans still alive are freed too (the reference leaks them)."""
+    """spmm_default/pytorch_api.cpp:162-164.  Plans still alive are freed too (the reference leaks them); handles
+    are never reused, so a front-end object that outlives the release just holds an unknown handle."""
     for h in list(_GROUPS):
         spmm_free_group(h)
+    _MANY_STATE.clear()
     _lib.check(_lib.lib().pygim_dpu_release())
     _STATE.update(initialised=False, nr_ranks=0)
 
@@ -121,15 +125,18 @@ def _to_device_group(fmt: int, row_indices, col_indices, values, nrows, ncols, d
     lib = _lib.lib()
     if on_gpu:
         torch.cuda.current_stream(vals[0].device).synchronize()   # borrowed arrays must be complete
+    # spmv: the `groups` single-column vectors of one call are ONE groups-wide tile for the library (one launch,
+    # A streamed once) - the per-vector list only describes the op's argument list
+    lib_cols = [int(h_size)] if variant == "spmv" else [int(c) for c in dense_cols]
     _lib.check(lib.pygim_spmm_to_device_group(
         fmt, DTYPE_CODE[dtype], n_sp, _ptr_array(rows), _ptr_array(cols), _ptr_array(vals), _i64_array(nrows),
-        _i64_array(ncols), _i64_array([v.numel() for v in vals]), len(dense_cols), _i64_array(dense_cols),
+        _i64_array(ncols), _i64_array([v.numel() for v in vals]), len(lib_cols), _i64_array(lib_cols),
         int(h_size), _lib.MEM_DEVICE if on_gpu else _lib.MEM_HOST, C.byref(handle)))
     dev = vals[0].device if on_gpu else torch.device("cuda", max(_cuda_device_index(), 0))
     _GROUPS[handle.value] = _GroupMeta(
         fmt=fmt, dtype=dtype, total_rows=int(nrows[0]), total_cols=int(sum(ncols)), h_size=int(h_size),
         dense_cols=[int(c) for c in dense_cols], device=dev, keep_alive=(rows + cols + vals) if on_gpu else [],
-        grande_cols=grande_cols, part_ncols=[int(c) for c in ncols], variant=variant)
+        grande_cols=grande_cols, part_ncols=[int(c) for c in ncols], variant=variant, lib_dense_cols=lib_cols)
     return int(handle.value)
 
 
@@ -170,6 +177,23 @@ def plan_set_option(handle: int, key: str, value: int) -> None:
     _lib.check(_lib.lib().pygim_plan_set_option(int(handle), key.encode(), int(value)))
 
 
+def plan_layout(handle: int, part: int = 0) -> dict:
+    out = (C.c_int64 * 6)()
+    _lib.check(_lib.lib().pygim_plan_layout(int(handle), int(part), out))
+    keys = ["items", "supertickets", "coo_runs_as_csr", "coo_sorted", "row_map", "unit_values"]
+    return dict(zip(keys, [int(v) for v in out]))
+
+
+def plan_set_row_map(handle: int, row_map: Optional[torch.Tensor]) -> None:
+    """Plan row r is row row_map[r] of the result (pygim_plan_set_row_map); None clears the map."""
+    if row_map is None:
+        _lib.check(_lib.lib().pygim_plan_set_row_map(int(handle), None, 0, _lib.MEM_HOST))
+        return
+    rm = row_map.to(torch.int32).contiguous()
+    _lib.check(_lib.lib().pygim_plan_set_row_map(int(handle), C.c_void_p(rm.data_ptr()), rm.numel(),
+                                                 _lib.MEM_DEVICE if rm.is_cuda else _lib.MEM_HOST))
+
+
 def plan_stats(handle: int, part: int = 0) -> dict:
     out = (C.c_int64 * 8)()
     _lib.check(_lib.lib().pygim_plan_stats(int(handle), int(part), out))
@@ -202,6 +226,12 @@ def _run_group(handle: int, B_parts: Sequence[torch.Tensor]) -> torch.Tensor:
     m = _meta(handle)
     if len(B_parts) != len(m.dense_cols):   # assert at pytorch_api.cpp:252
         raise _lib.PygimError("expected %d dense parts, got %d" % (len(m.dense_cols), len(B_parts)))
+    if m.lib_dense_cols is not None and m.lib_dense_cols != m.dense_cols:
+        # spmv: `groups` vectors [N x 1] -> one [N x groups] operand, one launch
+        for b in B_parts:
+            if b.dim() != 2 or b.size(1) != 1 or b.size(0) != m.total_cols:
+                raise _lib.PygimError("dense part has shape %s, expected (%d, 1)" % (tuple(b.shape), m.total_cols))
+        return spmm_run_dense(handle, torch.cat(list(B_parts), dim=1))
     B_parts = [b if b.stride(-1) == 1 or b.numel() == 0 else b.contiguous() for b in B_parts]
     for b, w in zip(B_parts, m.dense_cols):
         if b.dtype != m.dtype:
@@ -241,7 +271,8 @@ def spmm_coo_run_group(handle: int, B_parts: Sequence[torch.Tensor]) -> torch.Te
 
 def spmv_coo_run_group(handle: int, B_parts: Sequence[torch.Tensor]) -> torch.Tensor:
     """spmv_sparseP/pytorch_api.cpp:231-266: B_parts are `groups` vectors [N_pad x 1]; the result is
-    [N_pad x groups].  The vectors are computed together as one `groups`-column launch."""
+    [N_pad x groups].  The vectors are computed together as ONE `groups`-column launch (the plan holds a single
+    groups-wide tile, so A is streamed once per call, not once per vector)."""
     return _run_group(handle, B_parts)
 
 
@@ -277,7 +308,7 @@ def spmm_run_dense(handle: int, B: torch.Tensor, out: Optional[torch.Tensor] = N
         return out
     # host operand: present the column tiles as views of B (no copies) to the host entry point
     parts, col = [], 0
-    for w in m.dense_cols:
+    for w in (m.lib_dense_cols or m.dense_cols):
         parts.append(B[:, col:col + w])
         col += w
     out = torch.empty((m.total_rows, m.h_size), dtype=m.dtype) if out is None else _check_out(out, m, B)
@@ -287,27 +318,162 @@ def spmm_run_dense(handle: int, B: torch.Tensor, out: Optional[torch.Tensor] = N
     return out
 
 
-def spmm_run_dense_peers(handle: int, B: torch.Tensor, peer_ptrs: Sequence[int], multicast_ptr: int, ldc: int,
-                         row_offset: int) -> None:
-    """Row-sharded multi-GPU run with the all-gather fused into the kernel epilogue
-    (pygim_spmm_device_peers): this rank's rows are stored at `row_offset` of every peer's result matrix
-    (`peer_ptrs`: NVLink-mapped base pointers, own buffer included; `multicast_ptr`: NVSwitch multicast
-    mapping or 0).  Asynchronous on the current stream; the caller owns the cross-rank barriers."""
-    m = _meta(handle)
+def _dense_operand(m: _GroupMeta, B: torch.Tensor) -> torch.Tensor:
     if not B.is_cuda:
-        raise _lib.PygimError("the fused all-gather path needs a CUDA operand")
+        raise _lib.PygimError("this entry point needs a CUDA operand")
     if B.dtype != m.dtype or B.dim() != 2 or B.size(1) != m.h_size or B.size(0) != m.total_cols:
         raise _lib.PygimError("dense operand has shape %s/%s, expected (%d, %d) %s"
                               % (tuple(B.shape), B.dtype, m.total_cols, m.h_size, m.dtype))
     if B.stride(1) != 1 and B.numel():
         B = B.contiguous()
+    return B
+
+
+def spmm_run_dense_ex(handle: int, B: torch.Tensor, out: Optional[torch.Tensor] = None,
+                      scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                      residual_coeff: float = 1.0, peer_ptrs: Sequence[int] = (), multicast_ptr: int = 0,
+                      ldc: Optional[int] = None, row_offset: int = 0, peer_mask: Optional[torch.Tensor] = None,
+                      flag_ptrs: Sequence[int] = (), my_rank: int = 0, epoch: int = 0) -> Optional[torch.Tensor]:
+    """pygim_spmm_device_ex: the SpMM with the rest of a conv layer fused into its row store.
+    * `scale` (0-dim float32 CUDA tensor): float32 result = float(sum) * scale  (symmetric_dequantize);
+    * `residual` (float32 [rows x H]) and `residual_coeff`: result += coeff * residual  (GIN's (1+eps) x);
+    * `peer_ptrs` / `multicast_ptr` / `row_offset` / `peer_mask`: fused all-gather of a row-sharded run;
+    * `flag_ptrs` / `my_rank` / `epoch`: in-kernel arrival flags (see wait_flags).
+    Returns the result tensor (None for a peer run, whose result lives in the peers' buffers)."""
+    m = _meta(handle)
+    B = _dense_operand(m, B)
+    float_out = scale is not None or residual is not None
+    out_dtype = torch.float32 if float_out else m.dtype
+    epi = _lib.Epilogue()
+    keep = []
+    if scale is not None:
+        if not scale.is_cuda or scale.dtype != torch.float32 or scale.numel() != 1:
+            raise _lib.PygimError("scale must be a one-element float32 CUDA tensor")
+        epi.scale = scale.data_ptr()
+    if residual is not None:
+        if not residual.is_cuda or residual.dtype != torch.float32 or residual.dim() != 2 or \
+                residual.size(1) != m.h_size or residual.stride(1) != 1:
+            raise _lib.PygimError("residual must be a row-major float32 CUDA matrix with %d columns" % m.h_size)
+        epi.residual = residual.data_ptr()
+        epi.ld_residual = residual.stride(0) if residual.size(0) > 1 else max(m.h_size, 1)
+        epi.residual_coeff = float(residual_coeff)
+    n_peers = len(peer_ptrs)
+    if n_peers:
+        ptrs = (C.c_void_p * n_peers)(*[int(p) for p in peer_ptrs])
+        keep.append(ptrs)
+        epi.C_peers = ptrs
+        epi.n_peers = n_peers
+        epi.C_multicast = int(multicast_ptr) or None
+        epi.row_offset = int(row_offset)
+        if peer_mask is not None:
+            if not peer_mask.is_cuda or peer_mask.dtype != torch.uint8 or peer_mask.numel() != m.total_rows:
+                raise _lib.PygimError("peer_mask must be a uint8 CUDA vector with one entry per plan row")
+            epi.row_peer_mask = peer_mask.data_ptr()
+        if len(flag_ptrs):
+            fl = (C.c_void_p * n_peers)(*[int(p) for p in flag_ptrs])
+            keep.append(fl)
+            epi.flag_peers = fl
+            epi.my_rank = int(my_rank)
+            epi.epoch = int(epoch)
+        c_ptr, c_ld = None, int(ldc if ldc is not None else m.h_size)
+    else:
+        if out is None:
+            out = torch.empty((m.total_rows, m.h_size), dtype=out_dtype, device=B.device)
+        elif out.dtype != out_dtype or tuple(out.shape) != (m.total_rows, m.h_size) or not out.is_cuda or \
+                (out.numel() and out.stride(1) != 1):
+            raise _lib.PygimError("out= must be a row-major (%d, %d) %s CUDA tensor" % (m.total_rows, m.h_size, out_dtype))
+        c_ptr, c_ld = out.data_ptr(), (out.stride(0) if out.size(0) > 1 else max(m.h_size, 1))
     ldb = B.stride(0) if B.size(0) > 1 else max(B.size(1), 1)
-    ptrs = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
     with torch.cuda.device(B.device):
         stream = torch.cuda.current_stream(B.device).cuda_stream
-        _lib.check(_lib.lib().pygim_spmm_device_peers(int(handle), B.data_ptr(), ldb, ptrs, len(peer_ptrs),
-                                                      C.c_void_p(int(multicast_ptr) or None), int(ldc),
-                                                      int(row_offset), C.c_void_p(stream)))
+        _lib.check(_lib.lib().pygim_spmm_device_ex(int(handle), B.data_ptr(), ldb, c_ptr, c_ld, C.byref(epi),
+                                                   C.c_void_p(stream)))
+    return out if not n_peers else None
+
+
+def spmm_run_dense_peers(handle: int, B: torch.Tensor, peer_ptrs: Sequence[int], multicast_ptr: int, ldc: int,
+                         row_offset: int, **kw) -> None:
+    """Row-sharded multi-GPU run with the all-gather fused into the kernel epilogue: this rank's rows are stored at
+    `row_offset` of every peer's result matrix (`peer_ptrs`: NVLink-mapped base pointers, own buffer included;
+    `multicast_ptr`: NVSwitch multicast mapping or 0).  Asynchronous on the current stream; the caller owns the
+    cross-rank synchronisation (a barrier, or the arrival flags of spmm_run_dense_ex + wait_flags)."""
+    spmm_run_dense_ex(handle, B, peer_ptrs=peer_ptrs, multicast_ptr=multicast_ptr, ldc=ldc, row_offset=row_offset, **kw)
+
+
+def wait_flags(flags: torch.Tensor, epoch: int) -> None:
+    """Enqueue a wait on the current stream until every entry of the int32 CUDA vector `flags` has reached `epoch`."""
+    with torch.cuda.device(flags.device):
+        stream = torch.cuda.current_stream(flags.device).cuda_stream
+        _lib.check(_lib.lib().pygim_wait_flags(C.c_void_p(flags.data_ptr()), flags.numel(), int(epoch),
+                                               C.c_void_p(stream)))
+
+
+def quantize(x: torch.Tensor, dtype: torch.dtype):
+    """symmetric_quantize (models/quantize.py:20-38) in two kernels; returns (scale [0-dim float32], x_q).
+    Bit-identical to the torch expression for float32 input."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+        raise _lib.PygimError("quantize needs a 2-D float32 CUDA tensor")
+    if dtype not in (torch.int8, torch.int16, torch.int32, torch.float32):
+        raise _lib.PygimError("quantize supports INT8 / INT16 / INT32 / FLT32, got %s" % dtype)
+    if x.stride(1) != 1 and x.numel():
+        x = x.contiguous()
+    xq = torch.empty(x.shape, dtype=dtype, device=x.device)
+    scale = torch.empty((), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.lib().pygim_quantize(C.c_void_p(x.data_ptr()), x.size(0), x.size(1),
+                                             x.stride(0) if x.size(0) > 1 else max(x.size(1), 1), DTYPE_CODE[dtype],
+                                             C.c_void_p(xq.data_ptr()), max(x.size(1), 1), C.c_void_p(scale.data_ptr()),
+                                             C.c_void_p(stream)))
+    return scale, xq
+
+
+_MANY_STATE: dict = {}
+
+
+def spmm_run_dense_many(handles: Sequence[int], Bs: Sequence[torch.Tensor], outs: Sequence[torch.Tensor]) -> None:
+    """Several host-operand SpMMs (e.g. one per hidden size, or per layer) as ONE software pipeline: the upload of
+    operand k+1 and the download of result k-1 overlap the kernels of call k (three streams, one sync at the end).
+    `Bs` / `outs` are host tensors (pinned for full PCIe rate); results are complete when the call returns.  The
+    per-call host entry point (spmm_run_dense with a host operand) exposes the first upload and the last download of
+    EVERY call; this exposes them once per batch."""
+    assert len(handles) == len(Bs) == len(outs)
+    metas = [_meta(h) for h in handles]
+    dev = metas[0].device
+    st = _MANY_STATE.get(dev)
+    if st is None:
+        st = {"in": torch.cuda.Stream(dev), "out": torch.cuda.Stream(dev), "cmp": torch.cuda.Stream(dev), "buf": {}}
+        _MANY_STATE[dev] = st
+    cur = torch.cuda.current_stream(dev)
+    for s in (st["in"], st["cmp"], st["out"]):
+        s.wait_stream(cur)
+    staged = []
+    for h, m, B, out in zip(handles, metas, Bs, outs):
+        if B.is_cuda or out.is_cuda:
+            raise _lib.PygimError("spmm_run_dense_many takes host operands")
+        key = (int(h), tuple(B.shape), B.dtype)
+        if key not in st["buf"]:
+            st["buf"][key] = (torch.empty(B.shape, dtype=B.dtype, device=dev),
+                              torch.empty((m.total_rows, m.h_size), dtype=m.dtype, device=dev))
+        staged.append(st["buf"][key])
+    ev_in = []
+    with torch.cuda.stream(st["in"]):
+        for (Bd, _), B in zip(staged, Bs):
+            Bd.copy_(B, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(st["in"])
+            ev_in.append(e)
+    for k, (h, (Bd, Cd), out) in enumerate(zip(handles, staged, outs)):
+        st["cmp"].wait_event(ev_in[k])
+        with torch.cuda.stream(st["cmp"]):
+            spmm_run_dense(h, Bd, out=Cd)
+            e = torch.cuda.Event()
+            e.record(st["cmp"])
+        st["out"].wait_event(e)
+        with torch.cuda.stream(st["out"]):
+            out.copy_(Cd, non_blocking=True)
+    st["out"].synchronize()
+    cur.wait_stream(st["cmp"])
 
 
 def _grande_reassemble(m: _GroupMeta, B_parts: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -36,6 +36,7 @@ class SparseTensorCOO(SparseTensorBase):
             [p.crow_indices() for p in self.csr], [p.col_indices() for p in self.csr],
             [p.values() for p in self.csr], [p.size(0) for p in self.csr], [p.size(1) for p in self.csr],
             h_size, hidden_size)
+        self._plan_created()
 
     def to_pim_group_coo(self, hidden_size, B_parts=4):
         h_size = self._plan("COO", hidden_size, B_parts)
@@ -47,6 +48,7 @@ class SparseTensorCOO(SparseTensorBase):
         self.sp_info_ptr = pim_ops.spmm_coo_to_device_group(
             self.row_indices, self.col_indices, self.values, [p.size(0) for p in self.coo],
             [p.size(1) for p in self.coo], h_size, hidden_size)
+        self._plan_created()
 
     def to_pim_group(self, hidden_size, B_parts=4):
         if self.format == "COO":
@@ -67,9 +69,28 @@ class SparseTensorCOO(SparseTensorBase):
 
 
 def prepare_pim_spmm(adj_t, args):
+    """backend_pim/spmm.py:143-147.  Two optional attributes of `args` (absent in the reference's drivers, so they
+    run unchanged) switch on the prepare-time work SURVEY.md 8f lists: `reorder` ("cluster" | "degree"; also the
+    PYGIM_REORDER environment variable) permutes A's rows for L1 locality, and `tune` (True, or ds_parts == 0) lets
+    utils.autotuner pick the column tiling and the kernel options from the graph statistics."""
+    import os
+    method = getattr(args, "reorder", None) or os.environ.get("PYGIM_REORDER") or None
+    perm = None
+    if method and method != "none":
+        from ..reorder import reorder_rows
+        adj_t, perm, _ = reorder_rows(adj_t, method)
+    ds_parts, options = args.ds_parts, {}
+    if getattr(args, "tune", False) or not ds_parts:
+        from ..utils import autotuner
+        choice = autotuner.tune_plan(adj_t, args.hidden_size, args.data_type, args.sp_format,
+                                     cache_dir=getattr(args, "datadir", None), dataset=getattr(args, "dataset", None),
+                                     reordered=perm is not None)
+        ds_parts, options = choice["ds_parts"], choice["options"]
     A = SparseTensorCOO(adj_t, dtype=args.data_type, format=args.sp_format)
+    A.row_perm = perm
+    A.plan_options = options
     A.col_split(args.sp_parts)
-    A.to_pim_group(args.hidden_size, args.ds_parts)
+    A.to_pim_group(args.hidden_size, ds_parts)
     return A
 
 

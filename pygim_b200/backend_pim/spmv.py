@@ -3,8 +3,8 @@
 Follows backend_pim/spmv.py of the reference (SparseTensorCOO :21-109, prepare_pim_spmv :113-117,
 pim_spmv :119-120): COO only, matrix dims padded to a multiple of 64/bits, B cut into
 hidden/groups batches of `groups` columns, each batch handed to the SpMV op as `groups` vectors,
-padded rows cropped, batches concatenated.  The batch of vectors runs as one `groups`-column launch
-of the COO kernel.
+padded rows cropped, batches concatenated.  The batch of vectors runs as ONE `groups`-column launch
+(the library plans a single groups-wide tile; the per-vector width list only describes the op's arguments).
 """
 from __future__ import annotations
 
@@ -48,6 +48,7 @@ class SparseTensorCOO(SparseTensorBase):
         self.sp_info_ptr = pim_ops.spmv_coo_to_device_group(
             self.row_indices, self.col_indices, self.values, [p.size(0) for p in self.coo],
             [p.size(1) for p in self.coo], split_widths(hidden_size, hidden_size), hidden_size, rank_pre_spmv)
+        self._plan_created()
 
     def mul_single(self, B: torch.Tensor):
         assert self.hidden_size == B.size(1)

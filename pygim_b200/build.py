@@ -80,8 +80,9 @@ def _build(force: bool, verbose: bool, defines) -> str:
         obj = os.path.join(OBJ, "kernels_%s.o" % sfx)
         jobs.append((obj, [nvcc] + flags + ["-DPYGIM_T=" + ctype, "-DPYGIM_SFX=" + sfx, "-c",
                                             os.path.join(CSRC, "kernels_inst.cu"), "-o", obj]))
-    obj = os.path.join(OBJ, "backend_pim.o")
-    jobs.append((obj, [nvcc] + flags + ["-c", os.path.join(CSRC, "backend_pim.cu"), "-o", obj]))
+    for unit in ("backend_pim", "quantize"):
+        obj = os.path.join(OBJ, unit + ".o")
+        jobs.append((obj, [nvcc] + flags + ["-c", os.path.join(CSRC, unit + ".cu"), "-o", obj]))
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         for out in ex.map(lambda j: _run(j[1]), jobs):
             if verbose and out:

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "launch.h"
@@ -101,16 +102,18 @@ static int context_init(int device) {
 }
 
 // ------------------------------------------------------------------------------ plans
-// Second-level balancing of a CSR row range: rows longer than seg_len are cut into segments (built on the host
-// from rowptr).  `full` covers every row; the host entry point additionally keeps a few nnz-balanced row chunks
-// so that the download of chunk k overlaps the kernel of chunk k+1.
+// Second-level balancing of a CSR row range, built on the host from rowptr: work ITEMS in row order (a group of
+// consecutive short rows, or one seg_len-bounded segment of a long row) bundled into SUPERTICKETS of near-equal
+// nnz (spmm_csr.cuh).  `full` covers every row; the host entry point additionally keeps a few nnz-balanced row
+// chunks so that the download of chunk k overlaps the kernel of chunk k+1.
 struct CsrPlan {
     long long row_begin = 0, row_end = 0;
     Seg *d_segs = nullptr;
+    int2 *d_items = nullptr;
+    int *d_super_ptr = nullptr;
     int *d_long_rows = nullptr;
     int *d_long_seg_ptr = nullptr;
-    int *d_seg_count = nullptr;     // arrival counters, [count_chunks x n_long], zero between launches
-    int count_chunks = 0;
+    int n_items = 0, n_super = 0;
     int n_seg = 0, n_long = 0;
 };
 
@@ -121,32 +124,51 @@ struct SparsePart {
     const void *values = nullptr;
     bool owned = false;            // true: uploaded by us, freed in free_group
     bool unit_values = false;      // every stored value == 1 (checked on the device at plan time)
+    // COO: the stream is row-major sorted (checked on the device at plan time).  A sorted stream is run through
+    // the CSR kernels over a row pointer derived here once (d_rowptr); an unsorted one through the COO kernel with
+    // every flush atomic.
+    bool coo_sorted = true;
+    int *d_rowptr = nullptr;       // COO only: derived row pointer [nrows + 1] (owned)
     // CSR second-level balancing (built from rowptr on the host)
     std::vector<int> h_rowptr;     // host copy (kept for re-planning when seg_len changes)
     CsrPlan full;
     std::vector<CsrPlan> chunks;   // lazily built by the host entry point
     int seg_len = 0;
     long long max_row_nnz = 0, empty_rows = 0;
+    const int *csr_rowptr() const { return d_rowptr ? d_rowptr : rowidx; }
+};
+
+// Mutable launch state.  One per (plan, stream): launches on one stream are serialised, launches on different
+// streams get their own counters and partial-sum scratch, so one handle may be used from several streams.
+// Every counter is zero at rest (the last warp of a launch resets them), so the buffer can be shared by all
+// row-range plans of the group.
+struct Scratch {
+    cudaStream_t stream = nullptr;
+    int *counters = nullptr;        // [0] warps out, [4 ..) superticket draw counters, then long-row arrival counters
+    size_t n_counters = 0;
+    void *partial = nullptr;
+    size_t partial_bytes = 0;
+    unsigned long long *coo_ticket = nullptr;   // COO kernel: work counter + warps out
 };
 
 struct Group {
     int format = PYGIM_CSR;
     int dtype = PYGIM_FLT32;
     int device = 0;
+    bool csr_view = false;          // COO plan whose parts are all sorted: runs through the CSR kernels
     long long h_size = 0, total_rows = 0, total_cols = 0;
     std::vector<SparsePart> parts;
     std::vector<long long> dense_cols;
     // options (< 0 = automatic)
     long long opt_seg_len = -1, opt_l2_persist = -1, opt_chunk_nnz = -1, opt_rows_per_ticket = -1;
+    long long opt_item_nnz = -1, opt_super_nnz = -1, opt_max_g = -1, opt_cta_threads = -1;
     long long opt_unit_values = -1;   // 0 forces the general (weighted) kernels
     long long opt_short_rows = -1;    // 1/0 force the high-occupancy / deep-unroll CSR instantiation
     long long opt_host_chunks = -1;   // host entry point: row chunks for download/compute overlap (0 = off)
-    // dynamic work distribution of the persistent kernels: two device counters (tickets drawn, warps out) that
-    // the last warp of every launch zeroes again
-    unsigned long long *d_ticket = nullptr;
-    // scratch
-    void *d_partial = nullptr;
-    size_t partial_bytes = 0;
+    long long opt_coo_native = -1;    // 1: sorted COO streams also run through the COO kernel
+    int *d_row_map = nullptr;         // plan row r -> result row (row reordering); null = identity
+    std::mutex mu;                    // guards `scratch`
+    std::vector<Scratch> scratch;
     void *d_B = nullptr;   // staging for the host entry point
     void *d_C = nullptr;
     size_t dB_bytes = 0, dC_bytes = 0;
@@ -171,9 +193,10 @@ static int auto_seg_len(const SparsePart &p) {
 
 static void free_plan(CsrPlan &c) {
     if (c.d_segs) cudaFree(c.d_segs);
+    if (c.d_items) cudaFree(c.d_items);
+    if (c.d_super_ptr) cudaFree(c.d_super_ptr);
     if (c.d_long_rows) cudaFree(c.d_long_rows);
     if (c.d_long_seg_ptr) cudaFree(c.d_long_seg_ptr);
-    if (c.d_seg_count) cudaFree(c.d_seg_count);
     c = CsrPlan();
 }
 
@@ -183,52 +206,100 @@ static void free_csr_plan(SparsePart &p) {
     p.chunks.clear();
 }
 
-// Cut every row of [r0, r1) longer than seg_len into ceil(nnz/seg_len) near-equal segments.  Row ids are
-// relative to r0 (the kernel is handed rowptr + r0), nonzero offsets stay absolute.
-static int build_plan_range(const SparsePart &p, int seg_len, long long r0, long long r1, CsrPlan &out) {
+template <typename V> static int upload(V **dst, const std::vector<V> &src) {
+    *dst = nullptr;
+    if (src.empty()) return PYGIM_OK;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(dst), src.size() * sizeof(V)));
+    CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(V), cudaMemcpyHostToDevice));
+    return PYGIM_OK;
+}
+
+// Work items of the rows [r0, r1), in row order.  A row longer than seg_len becomes ceil(nnz/seg_len) near-equal
+// segments (their partial sums are merged in the kernel); shorter rows are grouped, item_nnz nonzeros or item_rows
+// rows per item, whichever comes first.  Row ids are relative to r0 (the kernel is handed rowptr + r0), nonzero
+// offsets stay absolute.  Items are then bundled into supertickets of about super_nnz nonzeros.
+static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, long long r0, long long r1, CsrPlan &out) {
     free_plan(out);
     out.row_begin = r0;
     out.row_end = r1;
     std::vector<Seg> segs;
+    std::vector<int2> items;
+    std::vector<long long> item_nnz;          // nonzeros per item (for the superticket cut)
     std::vector<int> long_rows, long_ptr;
     long_ptr.push_back(0);
     const std::vector<int> &rp = p.h_rowptr;
+    const long long mean = p.nrows > 0 ? p.nnz / std::max<long long>(p.nrows, 1) : 0;
+    const long long target = g.opt_item_nnz > 0 ? g.opt_item_nnz : 256;
+    const int max_rows = (int)std::max<long long>(1, std::min<long long>(31, g.opt_rows_per_ticket > 0 ? g.opt_rows_per_ticket : 31));
+    (void)mean;
+    int cur_first = -1, cur_cnt = 0;
+    long long cur_nnz = 0;
+    auto flush = [&]() {
+        if (cur_cnt > 0) {
+            items.push_back(make_int2(cur_first, cur_cnt));
+            item_nnz.push_back(cur_nnz);
+        }
+        cur_first = -1; cur_cnt = 0; cur_nnz = 0;
+    };
     for (long long r = r0; r < r1; ++r) {
         const long long s = (unsigned)rp[r], e = (unsigned)rp[r + 1];
         const long long n = e - s;
         if (n > seg_len) {
+            flush();
             const long long k = (n + seg_len - 1) / seg_len;
-            // equal pieces rounded up to a multiple of 32 so every piece but the last runs full batches
-            long long piece = ((n + k - 1) / k + 31) / 32 * 32;
+            // equal pieces rounded up to a multiple of 32 so every piece but the last runs full rounds
+            const long long piece = ((n + k - 1) / k + 31) / 32 * 32;
             for (long long b = s; b < e; b += piece) {
                 Seg sg;
                 sg.long_idx = (int)long_rows.size();
                 sg.start = (int)b;
                 sg.end = (int)std::min(e, b + piece);
                 sg.slot = (int)segs.size();
+                items.push_back(make_int2(~(int)segs.size(), 0));
+                item_nnz.push_back(sg.end - sg.start);
                 segs.push_back(sg);
             }
             long_rows.push_back((int)(r - r0));
             long_ptr.push_back((int)segs.size());
+        } else {
+            if (cur_cnt > 0 && (cur_nnz + n > target || cur_cnt >= max_rows)) flush();
+            if (cur_cnt == 0) cur_first = (int)(r - r0);
+            ++cur_cnt;
+            cur_nnz += n;
         }
     }
+    flush();
+    // supertickets: ~16 per SM, at least 2048 nonzeros (small graphs) and at most 128 K
+    long long total = 0;
+    for (long long v : item_nnz) total += v;
+    long long super = g.opt_super_nnz > 0 ? g.opt_super_nnz
+                                          : std::min<long long>(131072, std::max<long long>(2048, total / std::max(1, g_ctx.sm_count * 16)));
+    std::vector<int> super_ptr;
+    super_ptr.push_back(0);
+    long long acc = 0;
+    for (size_t k = 0; k < items.size(); ++k) {
+        acc += std::max<long long>(item_nnz[k], 1);
+        if (acc >= super || k + 1 == items.size()) {
+            super_ptr.push_back((int)k + 1);
+            acc = 0;
+        }
+    }
+    out.n_items = (int)items.size();
+    out.n_super = (int)super_ptr.size() - 1;
     out.n_seg = (int)segs.size();
     out.n_long = (int)long_rows.size();
+    int rc;
+    if ((rc = upload(&out.d_items, items))) return rc;
+    if (out.n_items > 0 && (rc = upload(&out.d_super_ptr, super_ptr))) return rc;
     if (out.n_seg > 0) {
-        // longest pieces first: tickets are handed out in index order
-        std::stable_sort(segs.begin(), segs.end(),
-                         [](const Seg &x, const Seg &y) { return (x.end - x.start) > (y.end - y.start); });
-        CUDA_TRY(cudaMalloc(&out.d_segs, segs.size() * sizeof(Seg)));
-        CUDA_TRY(cudaMemcpy(out.d_segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&out.d_long_rows, long_rows.size() * sizeof(int)));
-        CUDA_TRY(cudaMemcpy(out.d_long_rows, long_rows.data(), long_rows.size() * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMalloc(&out.d_long_seg_ptr, long_ptr.size() * sizeof(int)));
-        CUDA_TRY(cudaMemcpy(out.d_long_seg_ptr, long_ptr.data(), long_ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if ((rc = upload(&out.d_segs, segs)) || (rc = upload(&out.d_long_rows, long_rows)) ||
+            (rc = upload(&out.d_long_seg_ptr, long_ptr)))
+            return rc;
     }
     return PYGIM_OK;
 }
 
-static int build_csr_plan(SparsePart &p, int seg_len) {
+static int build_csr_plan(const Group &g, SparsePart &p, int seg_len) {
     free_csr_plan(p);
     p.seg_len = seg_len;
     p.max_row_nnz = 0;
@@ -238,23 +309,51 @@ static int build_csr_plan(SparsePart &p, int seg_len) {
         if (n > p.max_row_nnz) p.max_row_nnz = n;
         if (n == 0) ++p.empty_rows;
     }
-    return build_plan_range(p, seg_len, 0, p.nrows, p.full);
+    return build_plan_range(g, p, seg_len, 0, p.nrows, p.full);
 }
 
-static Group *as_group(pygim_handle_t h) { return reinterpret_cast<Group *>(static_cast<uintptr_t>(h)); }
+static int replan(Group *g) {
+    for (auto &p : g->parts) {
+        if (p.h_rowptr.empty()) continue;
+        int rc = build_csr_plan(*g, p, g->opt_seg_len > 0 ? (int)std::min<long long>(g->opt_seg_len, 1 << 30) : auto_seg_len(p));
+        if (rc) return rc;
+    }
+    return PYGIM_OK;
+}
+
+// Handles are never-reused ids into a registry (a freed handle can only ever be "unknown", never somebody
+// else's plan - the reference hands out raw pointers, pytorch_api.cpp:240).
+static std::mutex g_reg_mu;
+static std::unordered_map<uint64_t, Group *> g_registry;
+static uint64_t g_next_handle = 1;
+
+static Group *as_group(pygim_handle_t h) {
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    auto it = g_registry.find(h);
+    if (it == g_registry.end()) {
+        fail(PYGIM_ERR_INVALID, "unknown or freed plan handle %llu", (unsigned long long)h);
+        return nullptr;
+    }
+    return it->second;
+}
 
 static void destroy_group(Group *g) {
     if (!g) return;
     for (auto &p : g->parts) {
         free_csr_plan(p);
+        if (p.d_rowptr) cudaFree(p.d_rowptr);
         if (p.owned) {
             cudaFree(const_cast<int *>(p.rowidx));
             cudaFree(const_cast<int *>(p.colind));
             cudaFree(const_cast<void *>(p.values));
         }
     }
-    if (g->d_partial) cudaFree(g->d_partial);
-    if (g->d_ticket) cudaFree(g->d_ticket);
+    for (auto &sc : g->scratch) {
+        if (sc.counters) cudaFree(sc.counters);
+        if (sc.partial) cudaFree(sc.partial);
+        if (sc.coo_ticket) cudaFree(sc.coo_ticket);
+    }
+    if (g->d_row_map) cudaFree(g->d_row_map);
     if (g->d_B) cudaFree(g->d_B);
     if (g->d_C) cudaFree(g->d_C);
     for (auto &e : g->ev)
@@ -264,6 +363,64 @@ static void destroy_group(Group *g) {
     if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
     if (g->copy_in_stream) cudaStreamDestroy(g->copy_in_stream);
     delete g;
+}
+
+// The scratch of `stream` with at least n_counters zeroed ints and partial_bytes of partial-sum space.
+static int get_scratch(Group *g, cudaStream_t stream, size_t n_counters, size_t partial_bytes, bool coo, Scratch *out) {
+    std::lock_guard<std::mutex> lock(g->mu);
+    Scratch *sc = nullptr;
+    for (auto &c : g->scratch)
+        if (c.stream == stream) sc = &c;
+    if (!sc) {
+        g->scratch.emplace_back();
+        sc = &g->scratch.back();
+        sc->stream = stream;
+    }
+    if (n_counters > sc->n_counters) {
+        // grow-only; stream-ordered free keeps earlier launches of this stream valid
+        if (sc->counters) CUDA_TRY(cudaFreeAsync(sc->counters, stream));
+        const size_t n = std::max<size_t>(n_counters + n_counters / 2, 1024);
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc->counters), n * sizeof(int), stream));
+        CUDA_TRY(cudaMemsetAsync(sc->counters, 0, n * sizeof(int), stream));
+        sc->n_counters = n;
+    }
+    if (partial_bytes > sc->partial_bytes) {
+        if (sc->partial) CUDA_TRY(cudaFreeAsync(sc->partial, stream));
+        CUDA_TRY(cudaMallocAsync(&sc->partial, partial_bytes, stream));
+        sc->partial_bytes = partial_bytes;
+    }
+    if (coo && !sc->coo_ticket) {
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&sc->coo_ticket), 2 * sizeof(unsigned long long), stream));
+        CUDA_TRY(cudaMemsetAsync(sc->coo_ticket, 0, 2 * sizeof(unsigned long long), stream));
+    }
+    *out = *sc;       // a copy: the vector may grow under another thread
+    return PYGIM_OK;
+}
+
+// ---- sorted COO -> row pointer (type independent): rowptr[r] = first nonzero whose row is >= r
+__global__ void coo_check_sorted_kernel(const int *rowind, long long nnz, int nrows, int *flags) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rowind[i];
+        if (r < 0 || r >= nrows) flags[1] = 1;
+        if (i > 0 && rowind[i - 1] > r) flags[0] = 1;
+    }
+}
+__global__ void coo_rowptr_kernel(const int *rowind, long long nnz, int nrows, int *rowptr) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz; i += (long long)gridDim.x * blockDim.x) {
+        const int lo = i == 0 ? 0 : rowind[i - 1] + 1;
+        const int hi = i == nnz ? nrows : rowind[i];
+        for (int r = lo; r <= hi; ++r) rowptr[r] = (int)i;
+    }
+}
+// spins until every flag has reached `epoch` (the consumer side of the in-kernel arrival flags)
+__global__ void wait_flags_kernel(const int *flags, int n, int epoch) {
+    if ((int)threadIdx.x < n) {
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v - epoch < 0) __nanosleep(64);
+        } while (v - epoch < 0);
+    }
 }
 
 static cudaError_t dispatch_all_ones(int dtype, const void *val, long long n, int *flag) {
@@ -316,16 +473,10 @@ static void set_l2_window(cudaStream_t stream, const void *base, size_t span_byt
     (void)cudaGetLastError();
 }
 
-struct PeerDst {        // destinations of the fused all-gather (empty => plain local C)
-    int n = 0;
-    char *ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    char *mc = nullptr;
-};
-
-// C[:, col0:col0+w] (+)= A_i * B_tile[rows_i, :]  for one (sparse part, dense tile[, row range of the plan])
+// C[:, col0:col0+w] (+)= A_i * B_tile[rows_i, :]  for one (sparse part, dense tile[, row range of the plan]).
+// `epi` (optional) already points at this tile's columns; C is then float32 when it de-quantises / adds a residual.
 static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char *C, long long ldc, long long width,
-                    bool accumulate, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0,
-                    CsrPlan *plan = nullptr) {
+                    bool accumulate, cudaStream_t stream, const EpilogueLaunch *epi = nullptr, CsrPlan *plan = nullptr) {
     const size_t s = dtype_size(g->dtype);
     if (ldb < 0 || (unsigned long long)ldb * s >= (1ull << 32))
         return fail(PYGIM_ERR_INVALID, "row stride of the dense operand must be below 4 GiB");
@@ -341,65 +492,62 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         ~WindowGuard() { if (on) set_l2_window(st, nullptr, 0, 0); }
     } guard{stream, persist};
     cudaError_t err;
-    if (g->format == PYGIM_CSR) {
+    const bool float_out = epi && (epi->scale || epi->residual);
+    if (g->format == PYGIM_CSR || g->csr_view) {
         CsrPlan &pl = plan ? *plan : p.full;
-        if (pl.n_long > 0) {
-            // one arrival counter per (column chunk, long row); a column chunk is at most 32 words wide
-            const int chunks_needed = (int)((width + 31) / 32);
-            if (chunks_needed > pl.count_chunks) {
-                if (pl.d_seg_count) CUDA_TRY(cudaFreeAsync(pl.d_seg_count, stream));
-                const size_t bytes = (size_t)chunks_needed * (size_t)pl.n_long * sizeof(int);
-                CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&pl.d_seg_count), bytes, stream));
-                CUDA_TRY(cudaMemsetAsync(pl.d_seg_count, 0, bytes, stream));
-                pl.count_chunks = chunks_needed;
-            }
-        }
-        long long ldp = (width * (long long)s + 15) / 16 * 16 / (long long)s;
-        if (pl.n_seg > 0) {
-            const size_t need = (size_t)pl.n_seg * (size_t)ldp * s;
-            if (need > g->partial_bytes) {
-                // grow-only scratch; stream-ordered free keeps earlier launches valid
-                if (g->d_partial) CUDA_TRY(cudaFreeAsync(g->d_partial, stream));
-                CUDA_TRY(cudaMallocAsync(&g->d_partial, need, stream));
-                g->partial_bytes = need;
-            }
-        }
+        const long long ldp = (width * (long long)s + 15) / 16 * 16 / (long long)s;
+        const int max_g = g->opt_max_g > 0 ? (int)g->opt_max_g : 32;
+        const bool vec = csr_can_vectorize(s, B, C, float_out ? sizeof(float) : s, width, ldb, ldc, ldp);
+        const int chunks = csr_col_chunks(s, width, max_g, vec);
+        const size_t n_counters = 4 + (size_t)pl.n_super * chunks + (size_t)pl.n_long * chunks;
+        Scratch scratch;
+        Scratch *sc = &scratch;
+        int rc = get_scratch(g, stream, n_counters, (size_t)pl.n_seg * (size_t)ldp * s, false, sc);
+        if (rc) return rc;
         CsrLaunch l;
-        l.rowptr = p.rowidx + pl.row_begin;
+        l.rowptr = p.csr_rowptr() + pl.row_begin;
         l.colind = p.colind;
         l.val = p.values;
         l.B = B;
-        l.C = C + (size_t)pl.row_begin * (size_t)ldc * s;
-        l.partial = g->d_partial;
+        l.C = C;
+        l.partial = sc->partial;
         l.segs = pl.d_segs;
+        l.items = pl.d_items;
+        l.super_ptr = pl.d_super_ptr;
         l.long_rows = pl.d_long_rows;
         l.long_seg_ptr = pl.d_long_seg_ptr;
-        l.seg_count = pl.d_seg_count;
+        l.warps_out = reinterpret_cast<unsigned int *>(sc->counters);
+        l.super_cnt = sc->counters + 4;
+        l.seg_count = sc->counters + 4 + (size_t)pl.n_super * chunks;
+        l.n_super = pl.n_super;
+        l.n_items = pl.n_items;
         l.n_seg = pl.n_seg;
         l.n_long = pl.n_long;
         l.nrows = (int)(pl.row_end - pl.row_begin);
-        l.seg_len = p.seg_len;
-        // ~256 nonzeros per ticket: one row on Reddit-like graphs, 10 on products-like, 31 on citation graphs
-        l.rows_per_ticket = g->opt_rows_per_ticket > 0
-                                ? (int)g->opt_rows_per_ticket
-                                : (int)std::max<long long>(1, std::min<long long>(31, 256 * std::max<long long>(p.nrows, 1) /
-                                                                                     std::max<long long>(p.nnz, 1)));
+        l.nnz_total = p.nnz;
         l.short_rows = g->opt_short_rows >= 0 ? (int)g->opt_short_rows
                                               : (p.nnz < 96 * std::max<long long>(p.nrows, 1) ? 2 : 0);
+        l.max_g = max_g;
+        l.cta_threads = g->opt_cta_threads > 0 ? (int)g->opt_cta_threads : 256;
         l.ncols = width;
         l.ldb = ldb;
         l.ldc = ldc;
         l.ldp = ldp;
         l.accumulate = accumulate ? 1 : 0;
         l.unit_values = (p.unit_values && g->opt_unit_values != 0) ? 1 : 0;
-        l.n_peers = peers ? peers->n : 0;
-        l.mc = (peers && peers->mc) ? peers->mc + peer_off : nullptr;
-        for (int q = 0; q < 8; ++q) l.peers[q] = (peers && q < peers->n) ? peers->ptr[q] + peer_off : nullptr;
+        if (epi) l.epi = *epi;
+        if (g->d_row_map) l.epi.row_map = g->d_row_map + pl.row_begin;
+        if (l.epi.peer_mask) l.epi.peer_mask += pl.row_begin;
         l.sm_count = g_ctx.sm_count;
-        l.ticket = g->d_ticket;
         l.stream = stream;
         err = dispatch_csr(g->dtype, l, &g->last_launches);
     } else {
+        if (float_out || (epi && epi->n_peers > 0) || g->d_row_map)
+            return fail(PYGIM_ERR_INVALID, "fused epilogues / row maps need a CSR plan or a row-major sorted COO plan");
+        Scratch scratch;
+        Scratch *sc = &scratch;
+        int rc = get_scratch(g, stream, 0, 0, true, sc);
+        if (rc) return rc;
         CooLaunch l;
         l.rowind = p.rowidx;
         l.colind = p.colind;
@@ -414,9 +562,10 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.chunk_nnz = (int)g->opt_chunk_nnz;
         l.unit_values = (p.unit_values && g->opt_unit_values != 0) ? 1 : 0;
         l.accumulate = accumulate ? 1 : 0;
+        l.all_atomic = p.coo_sorted ? 0 : 1;
         l.n_warp_slots = g_ctx.sm_count * (g_ctx.max_threads_per_sm / 32);
         l.sm_count = g_ctx.sm_count;
-        l.ticket = g->d_ticket;
+        l.ticket = sc->coo_ticket;
         l.stream = stream;
         err = dispatch_coo(g->dtype, l, &g->last_launches);
     }
@@ -426,12 +575,17 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
 
 // The (sparse part x dense part) loop of spmm_pim_csr / spmm_host_*_group (ops.hpp:42-62):
 // dense part j of width h_j lands at column offset sum_{k<j} h_k; sparse part 0 overwrites, parts >= 1 add.
+// `epi` describes the whole result matrix; its pointers are advanced to each column tile here.
 static int run_group_device(Group *g, int n_ds, const void *const *B_parts, const long long *ldb, void *C,
-                            long long ldc, cudaStream_t stream, const PeerDst *peers = nullptr, size_t peer_off = 0,
-                            int chunk = -1) {
+                            long long ldc, cudaStream_t stream, const EpilogueLaunch *epi = nullptr, int chunk = -1) {
     if (n_ds != (int)g->dense_cols.size())
         return fail(PYGIM_ERR_INVALID, "expected %d dense parts, got %d", (int)g->dense_cols.size(), n_ds);
     const size_t s = dtype_size(g->dtype);
+    const bool float_out = epi && (epi->scale || epi->residual);
+    const size_t so = float_out ? sizeof(float) : s;
+    if (epi && (float_out || epi->n_peers > 0) && g->parts.size() != 1)
+        // partial products of sparse parts >= 1 would need a (remote) read-modify-write of a de-quantised value
+        return fail(PYGIM_ERR_INVALID, "fused epilogues (de-quantise, residual, all-gather) need sp_parts == 1");
     if (chunk <= 0) g->last_launches = 0;
     long long brow = 0;
     for (size_t i = 0; i < g->parts.size(); ++i) {
@@ -439,8 +593,19 @@ static int run_group_device(Group *g, int n_ds, const void *const *B_parts, cons
         for (int j = 0; j < n_ds; ++j) {
             const long long w = g->dense_cols[j];
             const char *B = static_cast<const char *>(B_parts[j]) + (size_t)brow * (size_t)ldb[j] * s;
-            char *Ct = static_cast<char *>(C) + (size_t)ccol * s;
-            int rc = run_tile(g, g->parts[i], B, ldb[j], Ct, ldc, w, i > 0, stream, peers, peer_off + (size_t)ccol * s,
+            char *Ct = C ? static_cast<char *>(C) + (size_t)ccol * so : nullptr;
+            EpilogueLaunch e;
+            if (epi) {
+                e = *epi;
+                for (int q = 0; q < e.n_peers; ++q) e.peers[q] = static_cast<char *>(e.peers[q]) + (size_t)ccol * so;
+                if (e.mc) e.mc = static_cast<char *>(e.mc) + (size_t)ccol * so;
+                if (e.residual) e.residual += ccol;
+                if (e.n_peers > 0) Ct = static_cast<char *>(e.peers[0]);
+                // only the LAST launch of the call announces the rows (flags are per call, not per tile)
+                if (!(i + 1 == g->parts.size() && j + 1 == n_ds))
+                    for (int q = 0; q < 8; ++q) e.flags[q] = nullptr;
+            }
+            int rc = run_tile(g, g->parts[i], B, ldb[j], Ct, ldc, w, i > 0, stream, epi ? &e : nullptr,
                               chunk >= 0 ? &g->parts[i].chunks[chunk] : nullptr);
             if (rc) return rc;
             ccol += w;
@@ -454,11 +619,13 @@ static int run_group_device(Group *g, int n_ds, const void *const *B_parts, cons
 
 using namespace pygim;
 
+int pygim_fail_invalid(const char *msg) { return fail(PYGIM_ERR_INVALID, "%s", msg); }
+
 // =============================================================================== C ABI
 extern "C" {
 
 PYGIM_API const char *pygim_last_error(void) { return g_err.c_str(); }
-PYGIM_API int pygim_abi_version(void) { return 1; }
+PYGIM_API int pygim_abi_version(void) { return 2; }
 
 PYGIM_API int pygim_dpu_init_ranks(int64_t nr_ranks, int64_t groups_per_rank, int device, int32_t *units_per_rank_out) {
     if (nr_ranks <= 0) return fail(PYGIM_ERR_INVALID, "nr_ranks must be positive, got %lld", (long long)nr_ranks);
@@ -596,26 +763,67 @@ PYGIM_API int pygim_spmm_to_device_group(int format, int dtype, int n_sp, const 
             }
             if ((long long)(unsigned)p.h_rowptr[(size_t)nrows[i]] != nnz[i] || p.h_rowptr[0] != 0)
                 return bail(fail(PYGIM_ERR_INVALID, "sparse part %d: rowptr does not span [0, nnz]", i));
-            int rc = build_csr_plan(p, auto_seg_len(p));
-            if (rc) return bail(rc);
+        } else {
+            // COO: is the stream row-major sorted (what spmm.py:40-42 `.coalesce()` yields)?  Row ids in range?
+            int *d_flags = nullptr, h_flags[2] = {0, 0};
+            cudaError_t e = cudaMalloc(&d_flags, 2 * sizeof(int));
+            if (e == cudaSuccess) e = cudaMemset(d_flags, 0, 2 * sizeof(int));
+            if (e == cudaSuccess && p.nnz > 0) {
+                coo_check_sorted_kernel<<<1184, 256>>>(p.rowidx, p.nnz, (int)p.nrows, d_flags);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpy(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost);
+            if (d_flags) cudaFree(d_flags);
+            if (e != cudaSuccess)
+                return bail(fail(PYGIM_ERR_CUDA, "sortedness scan of sparse part %d failed: %s", i, cudaGetErrorString(e)));
+            if (h_flags[1]) return bail(fail(PYGIM_ERR_INVALID, "sparse part %d: COO row index out of range", i));
+            p.coo_sorted = h_flags[0] == 0;
+            if (p.coo_sorted) {
+                // derive the row pointer once: a sorted COO stream then runs through the CSR kernels (rowind is
+                // not read again), an unsorted one keeps the COO kernel with every flush atomic
+                e = cudaMalloc(reinterpret_cast<void **>(&p.d_rowptr), ((size_t)p.nrows + 1) * sizeof(int));
+                if (e == cudaSuccess) {
+                    coo_rowptr_kernel<<<1184, 256>>>(p.rowidx, p.nnz, (int)p.nrows, p.d_rowptr);
+                    e = cudaGetLastError();
+                }
+                p.h_rowptr.resize((size_t)p.nrows + 1);
+                if (e == cudaSuccess)
+                    e = cudaMemcpy(p.h_rowptr.data(), p.d_rowptr, ((size_t)p.nrows + 1) * 4, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess)
+                    return bail(fail(PYGIM_ERR_CUDA, "row pointer of sparse part %d failed: %s", i, cudaGetErrorString(e)));
+            }
         }
     }
+    g->csr_view = format == PYGIM_COO;
+    for (auto &p : g->parts) g->csr_view = g->csr_view && p.coo_sorted;
+    if (format == PYGIM_COO && !g->csr_view)
+        for (auto &p : g->parts) { p.h_rowptr.clear(); }
     {
-        cudaError_t ce = cudaMalloc(&g->d_ticket, 2 * sizeof(unsigned long long));
-        if (ce == cudaSuccess) ce = cudaMemset(g->d_ticket, 0, 2 * sizeof(unsigned long long));
-        if (ce != cudaSuccess) return bail(fail(PYGIM_ERR_CUDA, "ticket counter setup failed: %s", cudaGetErrorString(ce)));
+        int rc = replan(g);
+        if (rc) return bail(rc);
     }
     for (auto &e : g->ev) {
         cudaError_t ce = cudaEventCreate(&e);
         if (ce != cudaSuccess) return bail(fail(PYGIM_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(ce)));
     }
-    *out_handle = static_cast<pygim_handle_t>(reinterpret_cast<uintptr_t>(g));
+    {
+        std::lock_guard<std::mutex> lock(g_reg_mu);
+        *out_handle = g_next_handle++;
+        g_registry[*out_handle] = g;
+    }
     return PYGIM_OK;
 }
 
 PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle) {
-    Group *g = as_group(handle);
-    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    Group *g = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_reg_mu);
+        auto it = g_registry.find(handle);
+        if (it == g_registry.end())
+            return fail(PYGIM_ERR_INVALID, "unknown or freed plan handle %llu", (unsigned long long)handle);
+        g = it->second;
+        g_registry.erase(it);
+    }
     cudaSetDevice(g->device);
     cudaDeviceSynchronize();
     destroy_group(g);
@@ -624,38 +832,54 @@ PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle) {
 
 PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int64_t value) {
     Group *g = as_group(handle);
-    if (!g || !key) return fail(PYGIM_ERR_INVALID, "null handle or key");
+    if (!g) return PYGIM_ERR_INVALID;
+    if (!key) return fail(PYGIM_ERR_INVALID, "null key");
+    bool rebuild = false;
     if (!std::strcmp(key, "seg_len")) {
-        g->opt_seg_len = value;
-        if (g->format == PYGIM_CSR) {
-            CUDA_TRY(cudaSetDevice(g->device));
-            CUDA_TRY(cudaDeviceSynchronize());
-            for (auto &p : g->parts) {
-                int rc = build_csr_plan(p, value > 0 ? (int)std::min<int64_t>(value, 1 << 30) : auto_seg_len(p));
-                if (rc) return rc;
-            }
-        }
+        g->opt_seg_len = value; rebuild = true;
+    } else if (!std::strcmp(key, "item_nnz")) {
+        g->opt_item_nnz = value; rebuild = true;
+    } else if (!std::strcmp(key, "super_nnz")) {
+        g->opt_super_nnz = value; rebuild = true;
+    } else if (!std::strcmp(key, "rows_per_ticket")) {
+        g->opt_rows_per_ticket = value; rebuild = true;
+    } else if (!std::strcmp(key, "max_g")) {
+        if (value > 0 && (value > 32 || (value & (value - 1)))) return fail(PYGIM_ERR_INVALID, "max_g must be a power of two <= 32");
+        g->opt_max_g = value;
+    } else if (!std::strcmp(key, "cta_threads")) {
+        if (value > 1024) return fail(PYGIM_ERR_INVALID, "cta_threads must be <= 1024");
+        g->opt_cta_threads = value;
     } else if (!std::strcmp(key, "l2_persist")) {
         g->opt_l2_persist = value;
     } else if (!std::strcmp(key, "chunk_nnz")) {
         g->opt_chunk_nnz = value;
-    } else if (!std::strcmp(key, "rows_per_ticket")) {
-        g->opt_rows_per_ticket = value;
     } else if (!std::strcmp(key, "unit_values")) {
         g->opt_unit_values = value;
     } else if (!std::strcmp(key, "short_rows")) {
         g->opt_short_rows = value;
     } else if (!std::strcmp(key, "host_chunks")) {
         g->opt_host_chunks = value;
+    } else if (!std::strcmp(key, "coo_native")) {
+        if (g->format != PYGIM_COO) return fail(PYGIM_ERR_INVALID, "coo_native applies to COO plans");
+        g->opt_coo_native = value;
+        bool sorted = true;
+        for (auto &p : g->parts) sorted = sorted && p.coo_sorted && p.d_rowptr;
+        g->csr_view = sorted && value <= 0;
     } else {
         return fail(PYGIM_ERR_INVALID, "unknown option '%s'", key);
+    }
+    if (rebuild && (g->format == PYGIM_CSR || g->csr_view)) {
+        CUDA_TRY(cudaSetDevice(g->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        return replan(g);
     }
     return PYGIM_OK;
 }
 
 PYGIM_API int pygim_plan_stats(pygim_handle_t handle, int part, int64_t *out8) {
     Group *g = as_group(handle);
-    if (!g || !out8) return fail(PYGIM_ERR_INVALID, "null handle or output");
+    if (!g) return PYGIM_ERR_INVALID;
+    if (!out8) return fail(PYGIM_ERR_INVALID, "null output");
     if (part < 0 || part >= (int)g->parts.size()) return fail(PYGIM_ERR_INVALID, "part %d out of range", part);
     const SparsePart &p = g->parts[part];
     out8[0] = p.nrows;
@@ -669,10 +893,52 @@ PYGIM_API int pygim_plan_stats(pygim_handle_t handle, int part, int64_t *out8) {
     return PYGIM_OK;
 }
 
+PYGIM_API int pygim_plan_layout(pygim_handle_t handle, int part, int64_t *out6) {
+    Group *g = as_group(handle);
+    if (!g) return PYGIM_ERR_INVALID;
+    if (!out6) return fail(PYGIM_ERR_INVALID, "null output");
+    if (part < 0 || part >= (int)g->parts.size()) return fail(PYGIM_ERR_INVALID, "part %d out of range", part);
+    const SparsePart &p = g->parts[part];
+    out6[0] = p.full.n_items;
+    out6[1] = p.full.n_super;
+    out6[2] = g->csr_view ? 1 : 0;
+    out6[3] = p.coo_sorted ? 1 : 0;
+    out6[4] = g->d_row_map ? 1 : 0;
+    out6[5] = p.unit_values ? 1 : 0;
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_plan_set_row_map(pygim_handle_t handle, const int32_t *row_map, int64_t n, int mem) {
+    Group *g = as_group(handle);
+    if (!g) return PYGIM_ERR_INVALID;
+    CUDA_TRY(cudaSetDevice(g->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (g->d_row_map) { cudaFree(g->d_row_map); g->d_row_map = nullptr; }
+    if (!row_map) return PYGIM_OK;
+    if (n != g->total_rows) return fail(PYGIM_ERR_INVALID, "row map has %lld entries, the plan has %lld rows", (long long)n, g->total_rows);
+    if (g->format == PYGIM_COO && !g->csr_view) return fail(PYGIM_ERR_INVALID, "row maps need a CSR plan or a row-major sorted COO plan");
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g->d_row_map), std::max<size_t>((size_t)n, 1) * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(g->d_row_map, row_map, (size_t)n * sizeof(int),
+                        mem == PYGIM_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    return PYGIM_OK;
+}
+
+// B as one matrix: the dense parts are its column tiles
+static void column_tiles(const Group *g, const void *B, int64_t ldb, std::vector<const void *> &parts, std::vector<long long> &lds) {
+    const size_t s = dtype_size(g->dtype);
+    parts.resize(g->dense_cols.size());
+    lds.assign(g->dense_cols.size(), ldb);
+    long long col = 0;
+    for (size_t j = 0; j < g->dense_cols.size(); ++j) {
+        parts[j] = static_cast<const char *>(B) + (size_t)col * s;
+        col += g->dense_cols[j];
+    }
+}
+
 PYGIM_API int pygim_spmm_run_group_device(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
                                 void *C, int64_t ldc, void *stream) {
     Group *g = as_group(handle);
-    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    if (!g) return PYGIM_ERR_INVALID;
     if (!B_parts || !ldb || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
     std::vector<long long> l(ldb, ldb + n_ds);
     return run_group_device(g, n_ds, B_parts, l.data(), C, ldc, static_cast<cudaStream_t>(stream));
@@ -680,47 +946,69 @@ PYGIM_API int pygim_spmm_run_group_device(pygim_handle_t handle, int n_ds, const
 
 PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ldb, void *C, int64_t ldc, void *stream) {
     Group *g = as_group(handle);
-    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    if (!g) return PYGIM_ERR_INVALID;
     if (!B || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
-    // the dense parts are column tiles of the one B matrix
-    const size_t s = dtype_size(g->dtype);
-    std::vector<const void *> parts(g->dense_cols.size());
-    std::vector<long long> lds(g->dense_cols.size(), ldb);
-    long long col = 0;
-    for (size_t j = 0; j < g->dense_cols.size(); ++j) {
-        parts[j] = static_cast<const char *>(B) + (size_t)col * s;
-        col += g->dense_cols[j];
-    }
+    std::vector<const void *> parts;
+    std::vector<long long> lds;
+    column_tiles(g, B, ldb, parts, lds);
     return run_group_device(g, (int)parts.size(), parts.data(), lds.data(), C, ldc, static_cast<cudaStream_t>(stream));
+}
+
+PYGIM_API int pygim_spmm_device_ex(pygim_handle_t handle, const void *B, int64_t ldb, void *C, int64_t ldc,
+                                   const pygim_epilogue_t *epi, void *stream) {
+    Group *g = as_group(handle);
+    if (!g) return PYGIM_ERR_INVALID;
+    if (!epi) return pygim_spmm_device(handle, B, ldb, C, ldc, stream);
+    if (!B) return fail(PYGIM_ERR_INVALID, "null buffer");
+    if (epi->n_peers < 0 || epi->n_peers > 8) return fail(PYGIM_ERR_INVALID, "n_peers must be 0..8, got %d", epi->n_peers);
+    if (epi->n_peers == 0 && !C) return fail(PYGIM_ERR_INVALID, "null result buffer");
+    if (epi->n_peers > 0 && !epi->C_peers) return fail(PYGIM_ERR_INVALID, "n_peers > 0 needs C_peers");
+    if (epi->residual && g->dtype != PYGIM_FLT32 && !epi->scale)
+        return fail(PYGIM_ERR_INVALID, "a residual needs a float32 result (FLT32 plan, or scale set)");
+    const bool float_out = epi->scale || epi->residual;
+    const size_t so = float_out ? sizeof(float) : dtype_size(g->dtype);
+    EpilogueLaunch e;
+    e.scale = epi->scale;
+    e.residual = epi->residual;
+    e.ld_res = epi->ld_residual;
+    e.coeff = epi->residual_coeff;
+    e.n_peers = epi->n_peers;
+    const size_t row_bytes = (size_t)epi->row_offset * (size_t)ldc * so;
+    for (int q = 0; q < epi->n_peers; ++q) {
+        if (!epi->C_peers[q]) return fail(PYGIM_ERR_INVALID, "peer %d has a null buffer", q);
+        e.peers[q] = static_cast<char *>(epi->C_peers[q]) + row_bytes;
+        e.flags[q] = epi->flag_peers ? epi->flag_peers[q] : nullptr;
+    }
+    e.mc = epi->C_multicast ? static_cast<char *>(epi->C_multicast) + row_bytes : nullptr;
+    e.peer_mask = epi->row_peer_mask;
+    e.my_rank = epi->my_rank;
+    e.epoch = epi->epoch;
+    if (e.residual) e.residual += (size_t)epi->row_offset * (size_t)e.ld_res;
+    std::vector<const void *> parts;
+    std::vector<long long> lds;
+    column_tiles(g, B, ldb, parts, lds);
+    return run_group_device(g, (int)parts.size(), parts.data(), lds.data(), C, ldc, static_cast<cudaStream_t>(stream), &e);
 }
 
 PYGIM_API int pygim_spmm_device_peers(pygim_handle_t handle, const void *B, int64_t ldb, void *const *C_peers,
                                       int n_peers, void *C_multicast, int64_t ldc, int64_t row_offset, void *stream) {
-    Group *g = as_group(handle);
-    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
-    if (!B || !C_peers) return fail(PYGIM_ERR_INVALID, "null buffer");
     if (n_peers < 1 || n_peers > 8) return fail(PYGIM_ERR_INVALID, "n_peers must be 1..8, got %d", n_peers);
-    if (g->format != PYGIM_CSR) return fail(PYGIM_ERR_INVALID, "the fused all-gather epilogue is CSR-only");
-    if (g->parts.size() != 1)   // partial products of sparse parts >= 1 would need a remote read-modify-write
-        return fail(PYGIM_ERR_INVALID, "the fused all-gather epilogue needs sp_parts == 1");
-    const size_t s = dtype_size(g->dtype);
-    PeerDst dst;
-    dst.n = n_peers;
-    const size_t row_bytes = (size_t)row_offset * (size_t)ldc * s;
-    for (int q = 0; q < n_peers; ++q) {
-        if (!C_peers[q]) return fail(PYGIM_ERR_INVALID, "peer %d has a null buffer", q);
-        dst.ptr[q] = static_cast<char *>(C_peers[q]) + row_bytes;
-    }
-    dst.mc = C_multicast ? static_cast<char *>(C_multicast) + row_bytes : nullptr;
-    std::vector<const void *> parts(g->dense_cols.size());
-    std::vector<long long> lds(g->dense_cols.size(), ldb);
-    long long col = 0;
-    for (size_t j = 0; j < g->dense_cols.size(); ++j) {
-        parts[j] = static_cast<const char *>(B) + (size_t)col * s;
-        col += g->dense_cols[j];
-    }
-    return run_group_device(g, (int)parts.size(), parts.data(), lds.data(), dst.ptr[0], ldc,
-                            static_cast<cudaStream_t>(stream), &dst, 0);
+    if (!C_peers) return fail(PYGIM_ERR_INVALID, "null buffer");
+    pygim_epilogue_t epi;
+    std::memset(&epi, 0, sizeof epi);
+    epi.C_peers = C_peers;
+    epi.n_peers = n_peers;
+    epi.C_multicast = C_multicast;
+    epi.row_offset = row_offset;
+    return pygim_spmm_device_ex(handle, B, ldb, nullptr, ldc, &epi, stream);
+}
+
+PYGIM_API int pygim_wait_flags(const int32_t *flags, int n, int32_t epoch, void *stream) {
+    if (!flags || n < 1 || n > 32) return fail(PYGIM_ERR_INVALID, "bad flag arguments");
+    wait_flags_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, n, epoch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PYGIM_ERR_CUDA, "wait_flags launch failed: %s", cudaGetErrorString(e));
+    return PYGIM_OK;
 }
 
 // Host entry point.  Software pipeline over three streams so that PCIe and the kernels overlap:
@@ -733,7 +1021,7 @@ PYGIM_API int pygim_spmm_device_peers(pygim_handle_t handle, const void *B, int6
 PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
                               void *C, int64_t ldc) {
     Group *g = as_group(handle);
-    if (!g) return fail(PYGIM_ERR_INVALID, "null handle");
+    if (!g) return PYGIM_ERR_INVALID;
     if (!B_parts || !ldb || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
     if (n_ds != (int)g->dense_cols.size())
         return fail(PYGIM_ERR_INVALID, "expected %d dense parts, got %d", (int)g->dense_cols.size(), n_ds);
@@ -781,7 +1069,7 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
 
     // ---- row chunks of the last tile (CSR only: COO chunks are nnz ranges, not row ranges)
     int n_chunks = 1;
-    if (pipelined && g->format == PYGIM_CSR && g->parts[0].nnz >= 4096 && rowsC >= 64) {
+    if (pipelined && (g->format == PYGIM_CSR || g->csr_view) && !g->d_row_map && g->parts[0].nnz >= 4096 && rowsC >= 64) {
         n_chunks = g->opt_host_chunks > 0 ? (int)g->opt_host_chunks : 4;
         if (g->parts[0].chunks.size() != (size_t)n_chunks) {
             std::vector<int64_t> split((size_t)n_chunks + 1);
@@ -791,7 +1079,7 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
                 for (auto &c : p.chunks) free_plan(c);
                 p.chunks.assign((size_t)n_chunks, CsrPlan());
                 for (int k = 0; k < n_chunks; ++k) {
-                    rc = build_plan_range(p, p.seg_len, split[k], split[k + 1], p.chunks[k]);
+                    rc = build_plan_range(*g, p, p.seg_len, split[k], split[k + 1], p.chunks[k]);
                     if (rc) return rc;
                 }
             }
@@ -842,7 +1130,7 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
                 const char *Bt = static_cast<const char *>(g->d_B) + tl.dev_off + (size_t)brow * tl.width * s;
                 char *Ct = static_cast<char *>(g->d_C) + tl.col0 * s;
                 int rc = run_tile(g, p, Bt, (long long)tl.width, Ct, (long long)H, (long long)tl.width, i > 0, st, nullptr,
-                                  0, chunks_here > 1 ? &p.chunks[k] : nullptr);
+                                  chunks_here > 1 ? &p.chunks[k] : nullptr);
                 if (rc) return rc;
                 brow += p.ncols;
             }
@@ -879,14 +1167,16 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
 
 PYGIM_API int pygim_last_timers(pygim_handle_t handle, double *out5_ms) {
     Group *g = as_group(handle);
-    if (!g || !out5_ms) return fail(PYGIM_ERR_INVALID, "null handle or output");
+    if (!g) return PYGIM_ERR_INVALID;
+    if (!out5_ms) return fail(PYGIM_ERR_INVALID, "null output");
     for (int i = 0; i < 5; ++i) out5_ms[i] = g->timers_ms[i];
     return PYGIM_OK;
 }
 
 PYGIM_API int pygim_last_launches(pygim_handle_t handle, int64_t *out) {
     Group *g = as_group(handle);
-    if (!g || !out) return fail(PYGIM_ERR_INVALID, "null handle or output");
+    if (!g) return PYGIM_ERR_INVALID;
+    if (!out) return fail(PYGIM_ERR_INVALID, "null output");
     *out = g->last_launches;
     return PYGIM_OK;
 }

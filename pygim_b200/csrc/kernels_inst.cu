@@ -15,106 +15,63 @@ namespace pygim {
 
 using T = PYGIM_T;
 
-static inline int align_bytes(const void *p) { return (int)(reinterpret_cast<uintptr_t>(p) & 15); }
-
-// 16-byte words when every row start is 16-byte aligned, single elements otherwise
-static bool can_vectorize(const void *B, const void *C, long long ncols, long long ldb, long long ldc, long long ldp) {
-    const long long s = (long long)sizeof(T);
-    return align_bytes(B) == 0 && align_bytes(C) == 0 && (ncols * s) % 16 == 0 && (ldb * s) % 16 == 0 &&
-           (ldc * s) % 16 == 0 && (ldp * s) % 16 == 0;
-}
-
-static int pow2_ceil(long long v) {
-    int g = 1;
-    while (g < v && g < 32) g <<= 1;
-    return g;
-}
-
-// Tuning knobs (overridable at build time for experiments: -DPYGIM_CSR_UNROLL=.. etc.)
-//   UNROLL     independent gathers per lane in flight before the first FMA
-//   R          index entries per lane per batch (batch = 32*R nonzeros); R*G >= UNROLL keeps UNROLL usable
-//   D          batches of the index stream prefetched ahead
-//   MIN_BLOCKS resident 256-thread blocks per SM the register allocation must allow
-#ifndef PYGIM_CSR_UNROLL
-#define PYGIM_CSR_UNROLL 8
+// Register budgets / gathers in flight per instantiation family (overridable at build time for experiments).
+//   NV         index vectors (4 nonzeros each) per lane in flight: 4*NV independent gathers before the first FMA
+//   THREADS    upper bound of the block size the launcher may pick (bounds the register allocation)
+//   MIN_BLOCKS resident blocks of THREADS threads per SM the register allocation must allow
+#ifndef PYGIM_CSR_NV
+#define PYGIM_CSR_NV 2
 #endif
-#ifndef PYGIM_CSR_MINBLOCKS
-#define PYGIM_CSR_MINBLOCKS 4
-#endif
-#ifndef PYGIM_CSR_PREFETCH
-#define PYGIM_CSR_PREFETCH 2
-#endif
-#ifndef PYGIM_NARROW_UNROLL
-#define PYGIM_NARROW_UNROLL 4
-#endif
-#ifndef PYGIM_NARROW_MINBLOCKS
-#define PYGIM_NARROW_MINBLOCKS 2
-#endif
-// 8/16-bit types carry E = 16/8 32-bit accumulators per lane: fewer gathers in flight and a larger register
-// budget keep those instantiations spill-free.
-template <int E, int G> struct CsrTune {
-    static constexpr int UNROLL = (E >= 8) ? PYGIM_NARROW_UNROLL : PYGIM_CSR_UNROLL;
-    static constexpr int R = (G >= UNROLL) ? 1 : ((UNROLL / G) > 4 ? 4 : (UNROLL / G));
-    static constexpr int D = (R > 1) ? 1 : PYGIM_CSR_PREFETCH;
-    static constexpr int MIN_BLOCKS =
-        (E >= 8) ? PYGIM_NARROW_MINBLOCKS : ((sizeof(T) * E >= 16) ? PYGIM_CSR_MINBLOCKS : 4);
+// default: 64 registers (one 1024-thread block, or four 256-thread blocks, per SM).  8/16-bit types carry
+// E = 16/8 32-bit accumulators per lane: 128 registers, four gathers in flight.  Weighted (non-unit) kernels
+// also hold the values of the nonzeros in flight: four gathers.
+template <int E, bool UNIT> struct CsrTune {
+    static constexpr int NV = (E >= 8 || !UNIT) ? 1 : PYGIM_CSR_NV;
+    static constexpr int THREADS = (E >= 8) ? 512 : 1024;
+    static constexpr int MIN_BLOCKS = 1;
 };
 // Short-row graphs (mean degree < ~100: ogbn-products, citation graphs) are bound by the dependent chain of one
 // row (index load -> gather -> shuffle tree -> store), not by gathers in flight: more resident warps win
 // (measured on products-shape: H=16 1.66 -> 0.93 ms, H=32 1.93 -> 1.34 ms, H=64 2.92 -> 2.36 ms).
-#ifndef PYGIM_SHORT_UNROLL
-#define PYGIM_SHORT_UNROLL 2
-#endif
-#ifndef PYGIM_SHORT_MINBLOCKS
-#define PYGIM_SHORT_MINBLOCKS 6
-#endif
-#ifndef PYGIM_SHORT_PREFETCH
-#define PYGIM_SHORT_PREFETCH 1
-#endif
-template <int E, int G> struct CsrTuneShort {
-    static constexpr int UNROLL = (E >= 8) ? PYGIM_NARROW_UNROLL : PYGIM_SHORT_UNROLL;
-    static constexpr int R = (G >= UNROLL) ? 1 : ((UNROLL / G) > 4 ? 4 : (UNROLL / G));
-    static constexpr int D = (R > 1) ? 1 : PYGIM_SHORT_PREFETCH;
-    static constexpr int MIN_BLOCKS = (E >= 8) ? PYGIM_NARROW_MINBLOCKS : ((G >= 32) ? PYGIM_CSR_MINBLOCKS : PYGIM_SHORT_MINBLOCKS);
-};
-// Streamed row tickets (short_rows == 2): 4 gathers of a run in flight, batches of 32 prefetched 2 ahead
-#ifndef PYGIM_STREAM_MINBLOCKS
-#define PYGIM_STREAM_MINBLOCKS 4
-#endif
-template <int E, int G> struct CsrTuneStream {
-    static constexpr int UNROLL = 4;
-    static constexpr int R = 1;
-    static constexpr int D = 2;
-    static constexpr int MIN_BLOCKS = PYGIM_STREAM_MINBLOCKS;
+template <int E, bool UNIT> struct CsrTuneShort {
+    static constexpr int NV = 1;
+    static constexpr int THREADS = 256;
+    static constexpr int MIN_BLOCKS = (E >= 8) ? 2 : 6;
 };
 // COO carries a third index stream and the run walker: one block less per SM than CSR keeps it spill-free
+#ifndef PYGIM_CSR_UNROLL
+#define PYGIM_CSR_UNROLL 8
+#endif
 template <int E, int G> struct CooTune {
-    static constexpr int UNROLL = CsrTune<E, G>::UNROLL;
-    static constexpr int R = CsrTune<E, G>::R;
-    static constexpr int D = CsrTune<E, G>::D;
-    static constexpr int MIN_BLOCKS = CsrTune<E, G>::MIN_BLOCKS > 3 ? 3 : CsrTune<E, G>::MIN_BLOCKS;
+    static constexpr int UNROLL = (E >= 8) ? 4 : PYGIM_CSR_UNROLL;
+    static constexpr int R = (G >= UNROLL) ? 1 : ((UNROLL / G) > 4 ? 4 : (UNROLL / G));
+    static constexpr int D = (R > 1) ? 1 : 2;
+    static constexpr int MIN_BLOCKS = (E >= 8) ? 2 : 3;
 };
-
 
 template <int E, int G, bool UNIT, typename Tune, bool STREAM = false>
 static cudaError_t launch_csr_t(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
-    auto kernel = csr_spmm_kernel<T, E, G, Tune::UNROLL, Tune::MIN_BLOCKS, Tune::R, Tune::D, UNIT, STREAM>;
-    static int blocks_per_sm = 0;   // per instantiation
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kCsrThreads, 0);
+    auto kernel = csr_spmm_kernel<T, E, G, Tune::NV, Tune::THREADS, Tune::MIN_BLOCKS, UNIT, STREAM>;
+    int threads = l.cta_threads > 0 ? l.cta_threads : 256;
+    threads = (threads + 31) / 32 * 32;
+    if (threads > Tune::THREADS) threads = Tune::THREADS;
+    static int blocks_per_sm[33] = {0};   // per instantiation, indexed by warps per block
+    int &bps = blocks_per_sm[threads / 32];
+    if (bps == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, 0);
         if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        if (bps < 1) bps = 1;
     }
     a.col_chunks = (a.nvec + G - 1) / G;
-    const unsigned long long total =
-        (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + (unsigned long long)a.n_row_tickets);
-    const unsigned long long warps_needed = total;
-    unsigned long long blocks = (unsigned long long)blocks_per_sm * (l.sm_count > 0 ? l.sm_count : 148);
-    const unsigned long long blocks_needed = (warps_needed + (kCsrThreads / 32) - 1) / (kCsrThreads / 32);
+    const int warps_per_block = threads / 32;
+    // no more warps than items (small graphs: a short grid drains and leaves faster)
+    const unsigned long long items = (unsigned long long)l.n_items * (unsigned long long)a.col_chunks;
+    unsigned long long blocks = (unsigned long long)bps * (l.sm_count > 0 ? l.sm_count : 148);
+    const unsigned long long blocks_needed = (items + warps_per_block - 1) / warps_per_block;
     if (blocks > blocks_needed) blocks = blocks_needed;
-    a.ticket = l.ticket;
-    a.n_warps = (unsigned)(blocks * (kCsrThreads / 32));
-    kernel<<<(unsigned)blocks, kCsrThreads, 0, l.stream>>>(a);
+    if (blocks < 1) blocks = 1;
+    a.n_warps = (unsigned)(blocks * warps_per_block);
+    kernel<<<(unsigned)blocks, threads, 0, l.stream>>>(a);
     ++*launches;
     return cudaGetLastError();
 }
@@ -124,10 +81,10 @@ static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t
     // the 16-byte-word instantiations of 32/64-bit types come in two register budgets (see CsrTuneShort)
     // (rows of 512 bytes and more - G == 32 - gain nothing from either: measured 5.11 vs 4.97 ms on products-shape)
     if constexpr (E < 8 && sizeof(T) * E >= 16 && G < 32) {
-        if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTuneStream<E, G>, true>(a, l, launches);   // streamed
-        if (l.short_rows) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, G>>(a, l, launches);
+        if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>, true>(a, l, launches);   // streamed
+        if (l.short_rows) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, UNIT>>(a, l, launches);
     }
-    return launch_csr_t<E, G, UNIT, CsrTune<E, G>>(a, l, launches);
+    return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>>(a, l, launches);
 }
 
 template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *launches) {
@@ -136,33 +93,52 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.colind = l.colind;
     a.val = static_cast<const T *>(l.val);
     a.B = static_cast<const T *>(l.B);
-    a.C = static_cast<T *>(l.C);
+    a.C = l.C;
     a.partial = static_cast<T *>(l.partial);
     a.segs = l.segs;
+    a.items = l.items;
+    a.super_ptr = l.super_ptr;
     a.long_rows = l.long_rows;
     a.long_seg_ptr = l.long_seg_ptr;
+    a.super_cnt = l.super_cnt;
     a.seg_count = l.seg_count;
+    a.warps_out = l.warps_out;
+    a.n_super = l.n_super;
     a.n_long = l.n_long;
     a.n_seg = l.n_seg;
     a.nrows = l.nrows;
-    a.seg_len = l.seg_len;
-    a.rows_per_ticket = l.rows_per_ticket < 1 ? 1 : (l.rows_per_ticket > 31 ? 31 : l.rows_per_ticket);
-    a.n_row_tickets = (l.nrows + a.rows_per_ticket - 1) / a.rows_per_ticket;
     a.nvec = (int)(l.ncols / E);
+    a.nnz_total = l.nnz_total;
+    {   // vector index loads need colind and val misaligned by the same number of ELEMENTS (mod 4)
+        const int mc = (int)((reinterpret_cast<uintptr_t>(l.colind) >> 2) & 3);
+        const int mv = (int)((reinterpret_cast<uintptr_t>(l.val) / sizeof(T)) & 3);
+        const bool ok = (reinterpret_cast<uintptr_t>(l.colind) & 3) == 0 && (l.unit_values || mc == mv);
+        a.idx_mis = ok ? mc : 4;
+    }
     a.ldb = l.ldb;
     a.ldb_bytes = (unsigned)(l.ldb * (long long)sizeof(T));
     a.ldc = l.ldc;
     a.ldp = l.ldp;
     a.accumulate = l.accumulate;
-    a.n_peers = l.n_peers;
-    a.mc = static_cast<T *>(l.mc);
-    for (int p = 0; p < kMaxPeers; ++p) a.peers[p] = p < l.n_peers ? static_cast<T *>(l.peers[p]) : nullptr;
-    const long long items = (long long)l.n_seg + l.nrows;
-    if (items == 0 || a.nvec == 0) return cudaSuccess;
+    a.epi.row_map = l.epi.row_map;
+    a.epi.scale = l.epi.scale;
+    a.epi.residual = l.epi.residual;
+    a.epi.ld_res = l.epi.ld_res;
+    a.epi.coeff = l.epi.coeff;
+    a.epi.mc = l.epi.mc;
+    a.epi.peer_mask = l.epi.peer_mask;
+    a.epi.n_peers = l.epi.n_peers;
+    a.epi.my_rank = l.epi.my_rank;
+    a.epi.epoch = l.epi.epoch;
+    for (int p = 0; p < kMaxPeers; ++p) {
+        a.epi.peers[p] = p < l.epi.n_peers ? l.epi.peers[p] : nullptr;
+        a.epi.flags[p] = p < l.epi.n_peers ? l.epi.flags[p] : nullptr;
+    }
+    if (l.n_items == 0 || a.nvec == 0) return cudaSuccess;
     cudaError_t err;
 #define PYGIM_CSR_CASE(GV) \
     case GV: err = l.unit_values ? launch_csr_g<E, GV, true>(a, l, launches) : launch_csr_g<E, GV, false>(a, l, launches); break
-    switch (pow2_ceil(a.nvec)) {
+    switch (csr_lanes(a.nvec, l.max_g)) {
         PYGIM_CSR_CASE(1);
         PYGIM_CSR_CASE(2);
         PYGIM_CSR_CASE(4);
@@ -189,7 +165,9 @@ cudaError_t PYGIM_CAT(check_all_ones_, PYGIM_SFX)(const void *val, long long n, 
 }
 
 cudaError_t PYGIM_CAT(launch_csr_, PYGIM_SFX)(const CsrLaunch &l, int64_t *launches) {
-    if (can_vectorize(l.B, l.C, l.ncols, l.ldb, l.ldc, l.ldp)) return launch_csr_e<16 / (int)sizeof(T)>(l, launches);
+    const size_t out_elem = (l.epi.scale || l.epi.residual) ? sizeof(float) : sizeof(T);
+    if (csr_can_vectorize(sizeof(T), l.B, l.C, out_elem, l.ncols, l.ldb, l.ldc, l.ldp))
+        return launch_csr_e<16 / (int)sizeof(T)>(l, launches);
     return launch_csr_e<1>(l, launches);
 }
 
@@ -228,6 +206,7 @@ template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *la
     a.ldc = l.ldc;
     a.nvec = (int)(l.ncols / E);
     a.accumulate = l.accumulate;
+    a.all_atomic = l.all_atomic;
     cudaError_t err;
     if (!l.accumulate && l.nrows > 0 && l.ncols > 0) {
         // the reference hands the kernels a torch::zeros result (pytorch_api.cpp:357-358)
@@ -249,7 +228,7 @@ template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *la
     a.n_chunks = (l.nnz + chunk - 1) / chunk;
 #define PYGIM_COO_CASE(GV) \
     case GV: return l.unit_values ? launch_coo_g<E, GV, true>(a, l, launches) : launch_coo_g<E, GV, false>(a, l, launches)
-    switch (pow2_ceil(a.nvec)) {
+    switch (csr_lanes(a.nvec, 32)) {
         PYGIM_COO_CASE(1);
         PYGIM_COO_CASE(2);
         PYGIM_COO_CASE(4);
@@ -261,7 +240,8 @@ template <int E> static cudaError_t launch_coo_e(const CooLaunch &l, int64_t *la
 }
 
 cudaError_t PYGIM_CAT(launch_coo_, PYGIM_SFX)(const CooLaunch &l, int64_t *launches) {
-    if (can_vectorize(l.B, l.C, l.ncols, l.ldb, l.ldc, 16)) return launch_coo_e<16 / (int)sizeof(T)>(l, launches);
+    if (csr_can_vectorize(sizeof(T), l.B, l.C, sizeof(T), l.ncols, l.ldb, l.ldc, 16))
+        return launch_coo_e<16 / (int)sizeof(T)>(l, launches);
     return launch_coo_e<1>(l, launches);
 }
 

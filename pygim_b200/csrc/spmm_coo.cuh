@@ -24,10 +24,23 @@
 // C is zero-filled by the launcher first (the reference's torch::zeros, pytorch_api.cpp:357-358)
 // unless accumulate is set.
 #pragma once
-#include "spmm_csr.cuh"   // release_tickets
 #include "vec.cuh"
 
 namespace pygim {
+
+// Every warp calls this once, after it drew its last (failing) ticket: the last warp out zeroes the counters, so
+// the plan needs no host-side bookkeeping between launches and a launch can be replayed from a CUDA graph.
+__device__ __forceinline__ void release_tickets(unsigned long long *ticket, unsigned int n_warps) {
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        const unsigned long long left = atomicAdd(ticket + 1, 1ULL);
+        if (left == (unsigned long long)n_warps - 1ULL) {
+            ticket[0] = 0ULL;
+            ticket[1] = 0ULL;
+            __threadfence();
+        }
+    }
+}
 
 template <typename T> struct CooArgs {
     const int *rowind;
@@ -45,6 +58,7 @@ template <typename T> struct CooArgs {
     int nvec;          // words (of E elements) per dense row
     int col_chunks;    // ceil(nvec / G)
     int accumulate;
+    int all_atomic;    // the stream is not row-major sorted: no row is owned by one warp, every flush is an atomic add
 };
 
 constexpr int kCooThreads = 256;
@@ -116,8 +130,8 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
 
     // does the neighbouring nonzero belong to the same row as our first / last one?
     const int first_row = a.rowind[cs];
-    const bool head_shared = cs > 0 && a.rowind[cs - 1] == first_row;
-    const bool tail_shared = ce < a.nnz && a.rowind[ce] == a.rowind[ce - 1];
+    const bool head_shared = a.all_atomic || (cs > 0 && a.rowind[cs - 1] == first_row);
+    const bool tail_shared = a.all_atomic || (ce < a.nnz && a.rowind[ce] == a.rowind[ce - 1]);
 
     Acc acc[E];
 #pragma unroll
@@ -163,7 +177,7 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
         // whole batch inside the current row?  (sorted stream: first and last entry decide)
         const int r_first = __shfl_sync(FULL, rr[0], 0);
         const int r_last = __shfl_sync(FULL, rr[R - 1], 31);
-        if (rem >= BATCH && r_first == cur && r_last == cur) {
+        if (rem >= BATCH && r_first == cur && r_last == cur && !a.all_atomic) {
 #pragma unroll
             for (int s0 = 0; s0 < STEPS; s0 += U) {
                 Pack<T, E> b[U];
@@ -190,7 +204,7 @@ __device__ __forceinline__ void coo_process_chunk(const CooArgs<T> &a, long long
                     const int row_here = __shfl_sync(FULL, rr[r], pos);
                     if (row_here != cur) {
                         coo_flush_row<T, E, G>(Ccol + (long long)cur * a.ldc, acc, writer,
-                                               !(cur == first_row && head_shared), accumulate);
+                                               !(cur == first_row && head_shared) && !a.all_atomic, accumulate);
                         cur = row_here;
                     }
                     const unsigned differs = __ballot_sync(FULL, lane >= pos && lane < left && rr[r] != row_here);

@@ -4,27 +4,32 @@
 // multigroup copies).  Where a DPU tasklet walks a contiguous row block and issues one MRAM read
 // of dense_size*byte_dt bytes per nonzero (:108-126), here:
 //
-//  * the grid is PERSISTENT (resident warps only); every warp pulls work items from a global,
-//    self-resetting (CUDA-graph friendly) ticket counter, so no warp idles while another still owns
-//    a long row (the reference's second-level balancing, partition_tsklt_by_nnz_csr,
-//    support/partition.c:186-229, made dynamic);
-//  * a work item is a group of 1..31 consecutive rows (about 256 nonzeros), or - for rows longer
-//    than seg_len - one seg_len-bounded segment of a row; segments come first, longest first;
-//  * the warp reads 32*R column indices and values per coalesced evict-first load, D batches ahead
-//    of the one being consumed, and hands them round with shuffles: the HBM latency of the index
-//    stream is off the critical path of the gathers.  The next ticket and its rowptr entries are
-//    fetched before the current item is processed;
+//  * WORK ITEMS are built once per plan, in row order: a group of 1..31 consecutive rows holding
+//    about item_nnz nonzeros, or - for rows longer than seg_len - one seg_len-bounded segment of a
+//    row (the reference's second-level balancing, partition_tsklt_by_nnz_csr,
+//    support/partition.c:186-229).  Consecutive items are bundled into SUPERTICKETS of near-equal
+//    nnz;
+//  * the grid is PERSISTENT and SM-AFFINE: SM s owns supertickets s, s + #SMs, s + 2 #SMs ... and
+//    every warp resident on it drains the same superticket (one atomic per item on the
+//    superticket's own counter), so the warps that share an SM's L1 work on neighbouring rows - with a locality
+//    preserving row order (prepare-time clustering, see pygim_b200/reorder.py) the dense rows they
+//    gather are L1 hits instead of L2 -> SM traffic.  Warps that run out of home work STEAL items
+//    from any unfinished superticket, so no warp idles while another still owns a long row;
 //  * a dense row of H elements is covered by G lanes, each moving one 16-byte word (float4,
-//    16 x int8, ...), so P = 32/G nonzeros are gathered by every load instruction and UNROLL
-//    independent gathers per lane are in flight before the first FMA consumes one.  The gather
-//    address is one IMAD.WIDE.U32 (32-bit byte stride, base held in registers);
+//    16 x int8, ...), so P = 32/G nonzeros are gathered by every load instruction.  Every lane
+//    group reads the column indices (and values) of ITS OWN four consecutive nonzeros as one
+//    16-byte vector load, one round ahead of the gathers that consume them - no shuffles on the
+//    gather path, 4 or 8 independent gathers per lane in flight.  The gather address is one
+//    IMAD.WIDE.U32 (32-bit byte stride, base held in registers);
 //  * the P partial sums are combined by an xor-shuffle tree in a fixed order (deterministic), and
 //    the row is written once with a streaming store - no host merge (memcpy_2D / memadd_2D,
-//    spmm_mul_csr.c:41-86) remains.  With peers set, the row goes to every GPU instead (fused
-//    all-gather over NVLink);
-//  * a segment publishes its partial sum; the last segment of a row to arrive adds the row's
-//    partials in slot order and writes the row (no second kernel, no floating-point atomics);
-//  * short-row graphs take csr_stream_rows: the consecutive rows of a ticket are ONE contiguous
+//    spmm_mul_csr.c:41-86) remains.  The store is also where the rest of a conv layer is fused:
+//    row un-permutation (row_map), integer -> float de-quantisation (scale), the (1+eps)*x
+//    residual, and - with peers set - the all-gather (the row goes to every GPU over NVLink);
+//  * a segment publishes its partial sum with a RELEASE (no L1 invalidation); the last segment of
+//    a row to arrive adds the row's partials in slot order and writes the row (no second kernel,
+//    no floating-point atomics);
+//  * short-row graphs take csr_stream_rows: the consecutive rows of an item are ONE contiguous
 //    nonzero stream, read in prefetched batches that ignore row boundaries and walked run by run;
 //  * UNIT: when the plan found every stored value equal to one, the value stream is not read.
 #pragma once
@@ -41,273 +46,146 @@ struct Seg {       // one nnz-bounded piece of a long row
     int slot;      // row of the partial buffer this piece writes (slots of one row are consecutive)
 };
 
+// what the row store does besides writing the sum (all optional, all decided per launch)
+struct Epilogue {
+    const int *row_map;        // plan row r is row row_map[r] of the result (row reordering); null = identity
+    const float *scale;        // device scalar: the result is FLOAT32, (float)sum * scale[0] (symmetric_dequantize)
+    const float *residual;     // float32 [rows x H], row stride ld_res: result += coeff * residual (GIN's (1+eps) x)
+    long long ld_res;
+    float coeff;
+    // fused all-gather (row-sharded multi-GPU): when n_peers > 0 every output row is stored to the same offset of
+    // every peer's C (NVLink-mapped pointers, the local one included) instead of C; when mc is set it is an
+    // NVSwitch multicast mapping of those buffers and ONE multimem.st reaches every GPU.  peer_mask (optional,
+    // one byte per plan row) restricts a row to the peers whose bit is set (halo exchange).
+    void *peers[kMaxPeers];
+    void *mc;
+    const unsigned char *peer_mask;
+    int n_peers;
+    // arrival flags: the last warp of the launch stores `epoch` into flags[p][my_rank] of every peer
+    int *flags[kMaxPeers];
+    int my_rank;
+    int epoch;
+};
+
 template <typename T> struct CsrArgs {
     const int *rowptr;
     const int *colind;
     const T *val;
     const T *B;        // dense input, row stride ldb elements
-    T *C;              // output, row stride ldc elements
-    T *partial;        // [n_seg x ldp] scratch for segment items
+    void *C;           // output (T, or float when epi.scale is set), row stride ldc elements
+    T *partial;        // [n_seg x ldp] scratch for segment items (ldp covers the whole dense row)
     const Seg *segs;
+    const int2 *items;          // x >= 0: rows [x, x + y);  x < 0: segment ~x
+    const int *super_ptr;       // [n_super + 1] items of superticket s are [ptr[s], ptr[s+1])
     const int *long_rows;       // [n_long] row id of every long row
     const int *long_seg_ptr;    // [n_long + 1] slots of long row i are [ptr[i], ptr[i+1])
-    int *seg_count;             // [col_chunks x n_long] arrival counters, zero between launches
-    int n_long;
-    unsigned long long *ticket;      // ticket[0]: work counter, ticket[1]: warps that have left the kernel;
-                                     // both are zero between launches (the last warp out resets them)
-    unsigned int n_warps;            // warps of this launch
-    int n_seg;
+    int *super_cnt;             // [n_super x col_chunks] items drawn per (superticket, column chunk); zero at rest
+    int *seg_count;             // [col_chunks x n_long] arrival counters, zero at rest
+    unsigned int *warps_out;    // warps that have left the kernel; zero at rest (the last one resets everything)
+    unsigned int n_warps;       // warps of this launch
+    int n_super, n_seg, n_long;
     int nrows;
-    int seg_len;       // rows with more nonzeros than this are handled through segs
-    int rows_per_ticket;   // short-row graphs: a ticket covers this many consecutive rows (1..31)
-    int n_row_tickets;     // ceil(nrows / rows_per_ticket)
     int nvec;          // words (of E elements) per dense row
     int col_chunks;    // ceil(nvec / G): every item is processed once per chunk of G words
+    long long nnz_total;        // entries of colind/val (bounds of the vector index loads)
+    int idx_mis;       // (address of colind / 4) mod 4 when val is misaligned the same way, else 4 = scalar index loads
     long long ldb, ldc, ldp;
     unsigned ldb_bytes; // ldb * sizeof(T) (< 4 GiB): 32-bit so a gather address is one IMAD.WIDE.U32
     int accumulate;    // 0: C = A*B, 1: C += A*B
-    // fused all-gather (row-sharded multi-GPU): when n_peers > 0 every output row is stored to the same
-    // offset of every peer's C (NVLink-mapped pointers, the local one included) instead of a.C; when mc is
-    // set it is an NVSwitch multicast mapping of those buffers and ONE multimem.st reaches every GPU.
-    T *peers[kMaxPeers];
-    T *mc;
-    int n_peers;
+    Epilogue epi;
 };
 
-constexpr int kCsrThreads = 256;
-
-// Every warp calls this once, after it drew its last (failing) ticket: the last warp out zeroes the counters, so
-// the plan needs no host-side bookkeeping between launches and a launch can be replayed from a CUDA graph.
-__device__ __forceinline__ void release_tickets(unsigned long long *ticket, unsigned int n_warps) {
-    if ((threadIdx.x & 31) == 0) {
-        __threadfence();
-        const unsigned long long left = atomicAdd(ticket + 1, 1ULL);
-        if (left == (unsigned long long)n_warps - 1ULL) {
-            ticket[0] = 0ULL;
-            ticket[1] = 0ULL;
-            __threadfence();
-        }
-    }
+// ---------------------------------------------------------------------------------------------- row store
+__device__ __forceinline__ void st_multimem(void *mc, long long byte_off, const float4 &f) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"((char *)mc + byte_off),
+                 "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w)
+                 : "memory");
 }
 
-// store one word of an output row to every destination of the fused all-gather
+template <typename T, int E> struct AccPack { typename Arith<T>::Acc v[E]; };
+
+// FLOAT32 result of one word: de-quantise (scale) and/or add coeff * residual.  One multiply, one multiply, one add,
+// never contracted, so the result equals torch's `out_q * scale + coeff * x` bit for bit
+// (models/quantize.py:40-42, pyg_gin_conv.py:84-86).  Out of line: runs once per row.
 template <typename T, int E>
-__device__ __forceinline__ void st_peers(T *const *peers, int n_peers, T *mc, long long off, const Pack<T, E> &v) {
-    if constexpr (sizeof(T) * E == 16) {
-        if (mc != nullptr) {
-            union { Pack<T, E> p; float4 f; } u;
-            u.p = v;
-            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + off),
-                         "f"(u.f.x), "f"(u.f.y), "f"(u.f.z), "f"(u.f.w)
-                         : "memory");
-            return;
-        }
-    }
-    for (int p = 0; p < n_peers; ++p) st_plain<T, E>(peers[p] + off, v);
-}
-
-struct CsrItem {
-    int long_idx;      // segment: its long row; rows: -1
-    int first;         // segment: slot of the partial buffer; rows: first row of the ticket
-    int count;         // rows covered (1 for a segment)
-    int rp;            // rows: lane l holds rowptr[first + l] (l <= count); segment: lane 0 start, lane 1 end
-    int chunk;         // column chunk
-    bool to_partial;
-};
-
-// tickets: col_chunks x (n_seg segment items, then n_row_tickets row groups)
-template <typename T>
-__device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, unsigned long long it) {
-    CsrItem r;
-    const int lane = threadIdx.x & 31;
-    const unsigned long long items = (unsigned long long)a.n_seg + (unsigned long long)a.n_row_tickets;
-    r.chunk = (int)(it / items);
-    const long long k = (long long)(it % items);
-    if (k < a.n_seg) {
-        const Seg sg = a.segs[k];
-        r.long_idx = sg.long_idx;
-        r.first = sg.slot;
-        r.count = 1;
-        r.rp = lane == 0 ? sg.start : sg.end;
-        r.to_partial = true;
-    } else {
-        r.long_idx = -1;
-        r.first = (int)(k - a.n_seg) * a.rows_per_ticket;
-        r.count = min(a.rows_per_ticket, a.nrows - r.first);
-        r.rp = a.rowptr[min(r.first + lane, a.nrows)];
-        r.to_partial = false;
-    }
-    return r;
-}
-
-// A segment of a long row has just published its partial sum.  The LAST segment of the row to arrive adds the
-// row's partials in slot order (fixed order => bitwise reproducible, no floating-point atomics) and writes the
-// final row.  Out of line on purpose: it runs once per segment and must not cost the gather loop registers.
-template <typename T, int E, int G>
-__device__ __noinline__ void csr_finish_long_row(const CsrArgs<T> &a, int chunk, int long_idx) {
-    using Acc = typename Arith<T>::Acc;
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / G;
-    const int vec = chunk * G + (lane % G);
-    const bool active = vec < a.nvec;
-    __threadfence();
-    __syncwarp();
-    int *counter = a.seg_count + (long long)chunk * a.n_long + long_idx;
-    int arrived = 0;
-    if (lane == 0) {
-        __threadfence();          // release: the warp's partial-sum stores (ordered by the barrier above) before the count
-        arrived = atomicAdd(counter, 1);
-    }
-    arrived = __shfl_sync(FULL, arrived, 0);
-    const int s0 = a.long_seg_ptr[long_idx], s1 = a.long_seg_ptr[long_idx + 1];
-    if (arrived != s1 - s0 - 1) return;
-    __threadfence();
-    if (lane == 0) *counter = 0;          // ready for the next launch
-    if (!(sub == 0 && active)) return;
-    Acc acc[E];
+__device__ __noinline__ void csr_emit_float(const CsrArgs<T> &a, AccPack<T, E> acc, int row, long long orow, int vec) {
+    const Epilogue &ep = a.epi;
+    const long long off = orow * a.ldc + (long long)vec * E;
+    float o[E];
+    const float s = ep.scale ? *ep.scale : 1.0f;
 #pragma unroll
-    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
-    for (int s = s0; s < s1; ++s)
-        add_old<T, E>(acc, ld_cg<T, E>(a.partial + (long long)s * a.ldp + (long long)vec * E));
-    const long long off = (long long)a.long_rows[long_idx] * a.ldc + (long long)vec * E;
-    if (a.n_peers > 0) {
-        st_peers<T, E>(a.peers, a.n_peers, a.mc, off, narrow<T, E>(acc));
-    } else {
-        if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(a.C + off));
-        st_stream<T, E>(a.C + off, narrow<T, E>(acc));
+    for (int k = 0; k < E; ++k) {
+        const float v = (float)(T)acc.v[k];
+        o[k] = ep.scale ? __fmul_rn(v, s) : v;
     }
-}
-
-// R = index entries held per lane per batch (a batch is 32*R nonzeros), D = batches prefetched ahead.
-// UNIT: the plan found every stored value equal to one (the value-less adjacency ToSparseTensor yields,
-// spmm.py:36-37) - the value stream is then neither loaded nor shuffled and the FMA degenerates to an add;
-// results are bit-identical to the general path (x * 1 is exact).
-template <typename T, int E, int G, int UNROLL, int R, int D, bool UNIT>
-__device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range_start, int range_end, int chunk,
-                                                  int dst_row, int long_idx) {
-    const bool to_partial = long_idx >= 0;
-    using Acc = typename Arith<T>::Acc;
-    using Shfl = typename Arith<T>::Shfl;
-    constexpr int P = 32 / G;
-    constexpr int BATCH = 32 * R;
-    constexpr int STEPS = G * R;                 // gather steps per full batch (P nonzeros each)
-    constexpr int U = (UNROLL < STEPS) ? UNROLL : STEPS;
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / G;
-    const int vec = chunk * G + (lane % G);
-    const bool active = vec < a.nvec;
-    const T *Bcol = a.B + (long long)vec * E;
-    asm volatile("" : "+l"(Bcol));     // keep the base in a register pair: gather address = one IMAD.WIDE.U32
-    const int end = range_end;
-
-    Acc acc[E];
+    if (ep.residual) {
+        const float *r = ep.residual + orow * ep.ld_res + (long long)vec * E;
 #pragma unroll
-    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
-
-    // index/value stream, prefetched D batches ahead of the gathers (evict-first: read once)
-    int nc[D][R];
-    Shfl nv[D][R];
+        for (int k = 0; k < E; ++k) o[k] = __fadd_rn(o[k], __fmul_rn(ep.coeff, r[k]));
+    }
+    float *Cf = static_cast<float *>(a.C);
+    if (ep.n_peers > 0) {
+        const unsigned m = ep.peer_mask ? ep.peer_mask[row] : 0xffu;
+        if constexpr (E % 4 == 0) {
+            if (ep.mc != nullptr && m == 0xffu) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int i = range_start + d * BATCH + r * 32 + lane;
-            nc[d][r] = 0;
-            nv[d][r] = 0;
-            if (i < end) {
-                nc[d][r] = ld_stream(a.colind + i);
-                if constexpr (!UNIT) nv[d][r] = ld_stream(a.val + i);
+                for (int q = 0; q < E / 4; ++q)
+                    st_multimem(ep.mc, (off + 4 * q) * 4, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+                return;
             }
         }
-    }
-    for (int base = range_start; base < end; base += BATCH) {
-        int c[R];
-        Shfl v[R];
+        for (int p = 0; p < ep.n_peers; ++p) {
+            if (!((m >> p) & 1u)) continue;
+            float *dst = static_cast<float *>(ep.peers[p]) + off;
 #pragma unroll
-        for (int r = 0; r < R; ++r) { c[r] = nc[0][r]; v[r] = nv[0][r]; }
-#pragma unroll
-        for (int d = 0; d + 1 < D; ++d) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) { nc[d][r] = nc[d + 1][r]; nv[d][r] = nv[d + 1][r]; }
+            for (int k = 0; k < E; ++k) dst[k] = o[k];
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int i = base + D * BATCH + r * 32 + lane;
-            nc[D - 1][r] = 0;
-            nv[D - 1][r] = 0;
-            if (i < end) {
-                nc[D - 1][r] = ld_stream(a.colind + i);
-                if constexpr (!UNIT) nv[D - 1][r] = ld_stream(a.val + i);
-            }
-        }
-        const int rem = end - base;
-        if (rem >= BATCH) {
-            // full batch: STEPS steps of P nonzeros, U gathers in flight per lane.
-            // step s covers batch entries s*P .. s*P+P-1 = register s/G, source lane (s%G)*P + sub
-#pragma unroll
-            for (int s0 = 0; s0 < STEPS; s0 += U) {
-                Pack<T, E> b[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int cc = __shfl_sync(FULL, c[(s0 + u) / G], ((s0 + u) % G) * P + sub);
-                    if (active) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    Shfl vv = (Shfl)1;
-                    if constexpr (!UNIT) vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
-                    if (active) fma_pack<T, E>(acc, b[u], vv);
-                }
-            }
-        } else {
-            // tail batch: per-lane predicate so padded slots never touch B (0 * inf would poison a row)
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int left = rem - r * 32;          // entries of register r that are real
-                if (left > 0) {
-                    const int steps = (min(left, 32) + P - 1) / P;
-                    for (int s = 0; s < steps; ++s) {
-                        const int src = s * P + sub;
-                        const int cc = __shfl_sync(FULL, c[r], src);
-                        Shfl vv = (Shfl)1;
-                        if constexpr (!UNIT) vv = __shfl_sync(FULL, v[r], src);
-                        if (active && src < left) {
-                            Pack<T, E> b = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
-                            fma_pack<T, E>(acc, b, vv);
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    // combine the P interleaved partial sums; fixed tree => bitwise reproducible
-#pragma unroll
-    for (int off = G; off < 32; off <<= 1) {
-#pragma unroll
-        for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
-    }
-    if (to_partial) {
-        if (sub == 0 && active)
-            st_plain<T, E>(a.partial + (long long)dst_row * a.ldp + (long long)vec * E, narrow<T, E>(acc));
-        csr_finish_long_row<T, E, G>(a, chunk, long_idx);     // rare path, kept out of line
         return;
     }
-    if (sub == 0 && active) {
-        if (a.n_peers > 0) {
-            st_peers<T, E>(a.peers, a.n_peers, a.mc, (long long)dst_row * a.ldc + (long long)vec * E,
-                           narrow<T, E>(acc));
-        } else {
-            T *p = a.C + (long long)dst_row * a.ldc + (long long)vec * E;
-            if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(p));
-            st_stream<T, E>(p, narrow<T, E>(acc));
-        }
+    if constexpr (E % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < E / 4; ++q)
+            __stcs(reinterpret_cast<float4 *>(Cf + off) + q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < E; ++k) __stcs(Cf + off + k, o[k]);
     }
 }
 
-// Write one finished row of a row ticket: combine the P interleaved partial sums (fixed xor tree) and store.
+// Store the E finished elements of (plan row `row`, word `vec`).  `acc` holds the full sums.
+template <typename T, int E>
+__device__ __forceinline__ void csr_emit(const CsrArgs<T> &a, typename Arith<T>::Acc (&acc)[E], int row, int vec) {
+    const Epilogue &ep = a.epi;
+    const long long orow = ep.row_map ? (long long)ep.row_map[row] : (long long)row;
+    if (ep.scale != nullptr || ep.residual != nullptr) {
+        AccPack<T, E> pk;
+#pragma unroll
+        for (int k = 0; k < E; ++k) pk.v[k] = acc[k];
+        csr_emit_float<T, E>(a, pk, row, orow, vec);
+        return;
+    }
+    const long long off = orow * a.ldc + (long long)vec * E;
+    T *C = static_cast<T *>(a.C);
+    if (ep.n_peers > 0) {
+        const unsigned m = ep.peer_mask ? ep.peer_mask[row] : 0xffu;
+        const Pack<T, E> v = narrow<T, E>(acc);
+        if constexpr (sizeof(T) * E == 16) {
+            if (ep.mc != nullptr && m == 0xffu) {
+                union { Pack<T, E> p; float4 f; } u;
+                u.p = v;
+                st_multimem(ep.mc, off * (long long)sizeof(T), u.f);
+                return;
+            }
+        }
+        for (int p = 0; p < ep.n_peers; ++p)
+            if ((m >> p) & 1u) st_plain<T, E>(static_cast<T *>(ep.peers[p]) + off, v);
+        return;
+    }
+    if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(C + off));
+    st_stream<T, E>(C + off, narrow<T, E>(acc));
+}
+
+// Combine the P interleaved partial sums (fixed xor tree => bitwise reproducible) and store the row.
 template <typename T, int E, int G>
 __device__ __forceinline__ void csr_store_row(const CsrArgs<T> &a, typename Arith<T>::Acc (&acc)[E], int row, int vec,
                                               bool writer) {
@@ -318,23 +196,194 @@ __device__ __forceinline__ void csr_store_row(const CsrArgs<T> &a, typename Arit
 #pragma unroll
         for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
     }
-    if (writer) {
-        const long long o = (long long)row * a.ldc + (long long)vec * E;
-        if (a.n_peers > 0) {
-            st_peers<T, E>(a.peers, a.n_peers, a.mc, o, narrow<T, E>(acc));
-        } else {
-            if (a.accumulate) add_old<T, E>(acc, ld_plain<T, E>(a.C + o));
-            st_stream<T, E>(a.C + o, narrow<T, E>(acc));
-        }
-    }
+    if (writer) csr_emit<T, E>(a, acc, row, vec);
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
 }
 
-// SHORT-ROW graphs: the rows [ja, jb) of a ticket are consecutive, so their nonzeros are ONE contiguous stream.
+// A segment of a long row has just published its partial sum.  The LAST segment of the row to arrive adds the
+// row's partials in slot order (fixed order => bitwise reproducible, no floating-point atomics) and writes the
+// final row.  Out of line on purpose: it runs once per segment and must not cost the gather loop registers.
+// Publishing is a RELEASE (MEMBAR without CCTL.IVALL): the SM's L1 - the whole point of the SM-affine schedule -
+// survives; only the one warp that merges a row pays an ACQUIRE, and it reads the partials past L1 anyway.
+template <typename T, int E, int G>
+__device__ __noinline__ void csr_finish_long_row(const CsrArgs<T> &a, int chunk, int long_idx) {
+    using Acc = typename Arith<T>::Acc;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int vec = chunk * G + (lane % G);
+    const bool active = vec < a.nvec;
+    __syncwarp();                 // the warp's partial-sum stores are ordered before lane 0's release
+    int *counter = a.seg_count + (long long)chunk * a.n_long + long_idx;
+    int arrived = 0;
+    if (lane == 0)
+        asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(arrived) : "l"(counter) : "memory");
+    arrived = __shfl_sync(FULL, arrived, 0);
+    const int s0 = a.long_seg_ptr[long_idx], s1 = a.long_seg_ptr[long_idx + 1];
+    if (arrived != s1 - s0 - 1) return;
+    asm volatile("fence.acquire.gpu;" ::: "memory");
+    if (lane == 0) *counter = 0;          // ready for the next launch
+    if (!(sub == 0 && active)) return;
+    Acc acc[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+    for (int s = s0; s < s1; ++s) add_old<T, E>(acc, ld_cg<T, E>(a.partial + (long long)s * a.ldp + (long long)vec * E));
+    csr_emit<T, E>(a, acc, a.long_rows[long_idx], vec);
+}
+
+// ---------------------------------------------------------------------------------------------- gather loops
+// one nonzero: gather word `vec` of dense row `col` and accumulate
+template <typename T, int E, bool UNIT>
+__device__ __forceinline__ void csr_one(const CsrArgs<T> &a, int i, const T *Bcol, typename Arith<T>::Acc (&acc)[E]) {
+    using Shfl = typename Arith<T>::Shfl;
+    const int c = __ldg(a.colind + i);
+    Shfl v = (Shfl)1;
+    if constexpr (!UNIT) v = (Shfl)__ldg(a.val + i);
+    const Pack<T, E> b = ld_dense<T, E>(row_ptr<T>(Bcol, c, a.ldb_bytes));
+    fma_pack<T, E>(acc, b, v);
+}
+
+// values of the four nonzeros of one aligned word
+template <typename T>
+__device__ __forceinline__ void ld_val4(const T *p, typename Arith<T>::Shfl (&v)[4]) {
+    using Shfl = typename Arith<T>::Shfl;
+    if constexpr (sizeof(T) == 8) {
+        const Pack<T, 2> v0 = ld_dense<T, 2>(p), v1 = ld_dense<T, 2>(p + 2);
+        v[0] = (Shfl)v0.e[0]; v[1] = (Shfl)v0.e[1]; v[2] = (Shfl)v1.e[0]; v[3] = (Shfl)v1.e[1];
+    } else {
+        const Pack<T, 4> vv = ld_dense<T, 4>(p);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (Shfl)vv.e[k];
+    }
+}
+
+// acc += sum over the nonzeros [start, end) of val * B[col, word `vec`].
+// The range is cut at the 16-byte boundaries of the index array: the (at most six) nonzeros before the first and
+// after the last boundary are handled one by one, the words in between are dealt round-robin to the P lane groups,
+// each group reading the four column indices (and values) of its word with ONE vector load.  NV words per group
+// are in flight: 4*NV independent gathers per lane before the first FMA, and the indices of the following NV words
+// are already loading.
+template <typename T, int E, int G, int NV, bool UNIT>
+__device__ __forceinline__ void csr_accumulate(const CsrArgs<T> &a, int start, int end, const T *Bcol, bool active,
+                                               typename Arith<T>::Acc (&acc)[E]) {
+    using Shfl = typename Arith<T>::Shfl;
+    constexpr int P = 32 / G;
+    const int sub = (threadIdx.x & 31) / G;
+    if (!active) return;
+    if (a.idx_mis >= 4) {           // colind / val not co-aligned (foreign views): element by element
+        for (int i = start + sub; i < end; i += P) csr_one<T, E, UNIT>(a, i, Bcol, acc);
+        return;
+    }
+    const int mis = a.idx_mis;
+    const int a0 = min(end, ((start + mis + 3) & ~3) - mis);     // first word boundary >= start
+    const int a1 = max(a0, ((end + mis) & ~3) - mis);            // last word boundary <= end
+    const int nw = (a1 - a0) >> 2;
+    const int4 *cw = reinterpret_cast<const int4 *>(a.colind + a0);
+    const T *vw = a.val + a0;
+
+    int w = sub;
+    int4 nx[NV];
+    Shfl nv[NV][4];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+        nx[n] = make_int4(0, 0, 0, 0);
+        if (w + n * P < nw) {
+            nx[n] = __ldcs(cw + w + n * P);
+            if constexpr (!UNIT) ld_val4<T>(vw + 4 * (w + n * P), nv[n]);
+        }
+    }
+    // edges (their latency overlaps the first words' index loads)
+    {
+        const int nh = a0 - start, ne = nh + (end - a1);
+        for (int e = sub; e < ne; e += P) csr_one<T, E, UNIT>(a, e < nh ? start + e : a1 + (e - nh), Bcol, acc);
+    }
+    for (; w + (NV - 1) * P < nw; w += NV * P) {
+        int4 c[NV];
+        Shfl v[NV][4];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            c[n] = nx[n];
+            if constexpr (!UNIT) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[n][k] = nv[n][k];
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            const int wn = w + (NV + n) * P;
+            if (wn < nw) {
+                nx[n] = __ldcs(cw + wn);
+                if constexpr (!UNIT) ld_val4<T>(vw + 4 * wn, nv[n]);
+            }
+        }
+        Pack<T, E> b[NV][4];
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            b[n][0] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].x, a.ldb_bytes));
+            b[n][1] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].y, a.ldb_bytes));
+            b[n][2] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].z, a.ldb_bytes));
+            b[n][3] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].w, a.ldb_bytes));
+        }
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fma_pack<T, E>(acc, b[n][k], UNIT ? (Shfl)1 : v[n][k]);
+        }
+    }
+    if constexpr (NV > 1) {
+        // fewer than NV words left for this lane group: one at a time (nx[0..] hold them in order)
+#pragma unroll
+        for (int n = 0; n < NV - 1; ++n) {
+            if (w + n * P < nw) {
+                Pack<T, E> b[4];
+                b[0] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].x, a.ldb_bytes));
+                b[1] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].y, a.ldb_bytes));
+                b[2] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].z, a.ldb_bytes));
+                b[3] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].w, a.ldb_bytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) fma_pack<T, E>(acc, b[k], UNIT ? (Shfl)1 : nv[n][k]);
+            }
+        }
+    }
+}
+
+// One row (or one segment of a long row): accumulate, combine the lane groups, store / publish.
+template <typename T, int E, int G, int NV, bool UNIT>
+__device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range_start, int range_end, int chunk,
+                                                  int dst_row, int long_idx) {
+    using Acc = typename Arith<T>::Acc;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int vec = chunk * G + (lane % G);
+    const bool active = vec < a.nvec;
+    const T *Bcol = a.B + (long long)vec * E;
+    asm volatile("" : "+l"(Bcol));     // keep the base in a register pair: gather address = one IMAD.WIDE.U32
+
+    Acc acc[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+    csr_accumulate<T, E, G, NV, UNIT>(a, range_start, range_end, Bcol, active, acc);
+
+    if (long_idx >= 0) {
+#pragma unroll
+        for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) acc[k] += __shfl_xor_sync(FULL, acc[k], off);
+        }
+        if (sub == 0 && active)
+            st_plain<T, E>(a.partial + (long long)dst_row * a.ldp + (long long)vec * E, narrow<T, E>(acc));
+        csr_finish_long_row<T, E, G>(a, chunk, long_idx);     // rare path, kept out of line
+        return;
+    }
+    csr_store_row<T, E, G>(a, acc, dst_row, vec, sub == 0 && active);
+}
+
+// SHORT-ROW graphs: the rows [ja, jb) of an item are consecutive, so their nonzeros are ONE contiguous stream.
 // It is read in prefetched 32-entry batches that ignore row boundaries (the index-load latency of a row is hidden
 // behind the rows before it) and walked run by run - a run being the part of a row inside the batch; row ends
-// come from the ticket's rowptr entries held in the lanes (`rp`: lane l holds rowptr[first + l]).
+// come from the item's rowptr entries held in the lanes (`rp`: lane l holds rowptr[first + l]).
 template <typename T, int E, int G, int UT, int D, bool UNIT>
 __device__ __forceinline__ void csr_stream_rows(const CsrArgs<T> &a, int first, int ja, int jb, int rp, int chunk) {
     using Acc = typename Arith<T>::Acc;
@@ -417,55 +466,131 @@ __device__ __forceinline__ void csr_stream_rows(const CsrArgs<T> &a, int first, 
     }
 }
 
-// Persistent grid: gridDim.x = resident blocks of the device.  Tickets run over
-// col_chunks * (n_seg + n_row_tickets) items, column chunk outermost.
-template <typename T, int E, int G, int UNROLL, int MIN_BLOCKS, int R, int D, bool UNIT, bool STREAM = false>
-__global__ void __launch_bounds__(kCsrThreads, MIN_BLOCKS) csr_spmm_kernel(const __grid_constant__ CsrArgs<T> a) {
+// ---------------------------------------------------------------------------------------------- scheduling
+struct CsrItem {
+    int long_idx;      // segment: its long row; rows: -1
+    int first;         // segment: slot of the partial buffer; rows: first row of the item
+    int count;         // rows covered (1 for a segment)
+    int rp;            // rows: lane l holds rowptr[first + l] (l <= count); segment: lane 0 start, other lanes end
+};
+
+template <typename T> __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, int idx) {
+    CsrItem r;
+    const int lane = threadIdx.x & 31;
+    const int2 it = __ldg(a.items + idx);
+    if (it.x < 0) {
+        const Seg sg = a.segs[~it.x];
+        r.long_idx = sg.long_idx;
+        r.first = sg.slot;
+        r.count = 1;
+        r.rp = lane == 0 ? sg.start : sg.end;
+    } else {
+        r.long_idx = -1;
+        r.first = it.x;
+        r.count = it.y;
+        r.rp = a.rowptr[min(it.x + lane, a.nrows)];
+    }
+    return r;
+}
+
+// Every warp calls this once, when it has found no more work: the last warp out zeroes the counters (the plan
+// needs no host-side bookkeeping between launches; a launch can be replayed from a CUDA graph) and - in a
+// row-sharded multi-GPU launch - tells every peer that this rank's rows have landed.
+template <typename T> __device__ __forceinline__ void csr_leave(const CsrArgs<T> &a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned long long total =
-        (unsigned long long)a.col_chunks * ((unsigned long long)a.n_seg + (unsigned long long)a.n_row_tickets);
+    __syncwarp();
+    unsigned left = 0;
+    if (lane == 0) {
+        if (a.epi.n_peers > 0) __threadfence_system();      // this warp's peer / multimem stores before the count
+        else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        left = atomicAdd(a.warps_out, 1u);
+    }
+    left = __shfl_sync(FULL, left, 0);
+    if (left != a.n_warps - 1u) return;
+    const int n = a.n_super * a.col_chunks;
+    for (int i = lane; i < n; i += 32) a.super_cnt[i] = 0;
+    if (lane == 0) *a.warps_out = 0u;
+    if (a.epi.n_peers > 0 && a.epi.flags[0] != nullptr) {
+        __threadfence_system();           // every warp's rows (observed through the counter) before the flags
+        if (lane < a.epi.n_peers)
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(a.epi.flags[lane] + a.epi.my_rank), "r"(a.epi.epoch)
+                         : "memory");
+    }
+}
 
-    auto take_ticket = [&]() -> unsigned long long {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.ticket, 1ULL);
-        return __shfl_sync(FULL, t, 0);
-    };
+// Persistent, SM-affine grid.  (superticket s, column chunk c) has index s * col_chunks + c.
+// THREADS only bounds the register allocation: the launcher picks the block size (256 .. THREADS).
+template <typename T, int E, int G, int NV, int THREADS, int MIN_BLOCKS, bool UNIT, bool STREAM = false>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __grid_constant__ CsrArgs<T> a) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int n_units = a.n_super * a.col_chunks;
 
-    unsigned long long it = take_ticket();
-    CsrItem cur;
-    if (it < total) cur = csr_load_item<T>(a, it);
-    while (it < total) {
-        // look ahead: the next ticket and its row bounds are in flight while this item is processed
-        const unsigned long long nit = take_ticket();
-        CsrItem nxt;
-        if (nit < total) nxt = csr_load_item<T>(a, nit);
-        if (STREAM && !cur.to_partial) {
-            // rows longer than seg_len are covered by their segments: stream the row blocks between them
-            const int deg = __shfl_down_sync(FULL, cur.rp, 1) - cur.rp;
-            unsigned long_rows = __ballot_sync(FULL, lane < cur.count && deg > a.seg_len);
-            int ja = 0;
-            while (ja < cur.count) {
-                const unsigned rest = long_rows >> ja;
-                const int jb = rest ? ja + (__ffs(rest) - 1) : cur.count;
-                if (jb > ja)
-                    csr_stream_rows<T, E, G, (UNROLL < 4 ? UNROLL : 4), (D < 2 ? 2 : D), UNIT>(a, cur.first, ja, jb, cur.rp,
-                                                                                             cur.chunk);
-                ja = jb + 1;
-            }
+    auto process = [&](const CsrItem &cur, int chunk) {
+        if (STREAM && cur.long_idx < 0) {
+            csr_stream_rows<T, E, G, 4, 2, UNIT>(a, cur.first, 0, cur.count, cur.rp, chunk);
+        } else if (cur.long_idx >= 0) {
+            csr_process_range<T, E, G, NV, UNIT>(a, __shfl_sync(FULL, cur.rp, 0), __shfl_sync(FULL, cur.rp, 1), chunk,
+                                                 cur.first, cur.long_idx);
         } else {
             for (int j = 0; j < cur.count; ++j) {
                 const int start = __shfl_sync(FULL, cur.rp, j);
                 const int end = __shfl_sync(FULL, cur.rp, j + 1);
-                // rows longer than seg_len are covered by their segments + the last-arriver merge
-                if (cur.to_partial || end - start <= a.seg_len)
-                    csr_process_range<T, E, G, UNROLL, R, D, UNIT>(a, start, end, cur.chunk, cur.first + j, cur.long_idx);
+                csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.first + j, -1);
             }
         }
-        it = nit;
-        cur = nxt;
+    };
+
+    // drain one (superticket, chunk): one atomic per item, the next item is drawn (and its descriptor loaded)
+    // before the current one is processed
+    auto drain = [&](int unit) {
+        const int s = unit / a.col_chunks, chunk = unit - s * a.col_chunks;
+        const int lo = a.super_ptr[s], n = a.super_ptr[s + 1] - lo;
+        int *cnt = a.super_cnt + unit;
+        auto take = [&]() -> int {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(cnt, 1);
+            return __shfl_sync(FULL, t, 0);
+        };
+        int it = take();
+        CsrItem cur;
+        if (it < n) cur = csr_load_item<T>(a, lo + it);
+        while (it < n) {
+            const int nit = take();
+            CsrItem nxt;
+            if (nit < n) nxt = csr_load_item<T>(a, lo + nit);
+            process(cur, chunk);
+            it = nit;
+            cur = nxt;
+        }
+    };
+
+    // home supertickets: keyed by the SM, not by the block, so every block resident on an SM drains the same ones
+    unsigned smid, nsmid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm("mov.u32 %0, %%nsmid;" : "=r"(nsmid));
+    for (int unit = (int)smid; unit < n_units; unit += (int)nsmid) drain(unit);
+    // steal: any (superticket, chunk) that still has undrawn items, scanning from an SM-specific offset
+    {
+        const int base = (int)(((unsigned long long)smid * 2654435761ull) % (unsigned)n_units);
+        for (int o = 0; o < n_units; o += 32) {
+            int u = base + o + lane;
+            if (u >= n_units) u -= n_units;
+            bool open = false;
+            if (o + lane < n_units) {
+                const int s = u / a.col_chunks;
+                open = *(volatile int *)(a.super_cnt + u) < a.super_ptr[s + 1] - a.super_ptr[s];
+            }
+            unsigned m = __ballot_sync(FULL, open);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                drain(__shfl_sync(FULL, u, src));
+            }
+        }
     }
-    release_tickets(a.ticket, a.n_warps);
+    csr_leave<T>(a);
 }
 
 }  // namespace pygim

@@ -119,6 +119,63 @@ def synthetic_csr(n: int, nnz: int, max_deg: int, ncols: Optional[int] = None, s
     return rowptr, col
 
 
+def clustered_csr(n: int, nnz: int, max_deg: int, seed: int = 0, device: str = "cpu", community: int = 1024,
+                  p_in: float = 0.7, hidden_order: bool = True, deg: Optional[torch.Tensor] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Same N, nnz and degree sequence as synthetic_csr, but with COMMUNITY STRUCTURE (a stochastic block model):
+    nodes form communities of `community` members and a row draws round(p_in * degree) of its neighbours inside
+    its own community (as many as fit), the rest uniformly from all other nodes.  Real graphs of this kind (Reddit:
+    posts of one subreddit; products: one category) look like this; synthetic_csr deliberately does not.
+
+    With `hidden_order` the node ids are a random permutation of the community layout - like a real dataset the
+    structure is there but not visible in the numbering, so a locality-aware pipeline has to FIND it
+    (pygim_b200/reorder.py).  hidden_order=False numbers the nodes community by community (the best case a
+    reordering can reach)."""
+    if deg is None:
+        deg = degree_sequence(n, nnz, max_deg, n, seed)
+    g = torch.Generator().manual_seed(seed + 17)
+    pi = torch.randperm(n, generator=g) if hidden_order else torch.arange(n)      # layout position -> node id
+    pos_of = torch.empty(n, dtype=torch.int64)
+    pos_of[pi] = torch.arange(n)                                                   # node id -> layout position
+    deg = deg.to(device)
+    pi_d, pos_d = pi.to(device), pos_of.to(device)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    gen = torch.Generator(device=device).manual_seed(seed + 1)
+    col = torch.empty(int(rowptr[-1]), dtype=torch.int64, device=device)
+    n_comm = max(1, (n + community - 1) // community)
+    rows_per_chunk = max(1, int(n * (16_000_000 / max(nnz, 1))))
+    for r0 in range(0, n, rows_per_chunk):
+        r1 = min(n, r0 + rows_per_chunk)
+        e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+        if e1 == e0:
+            continue
+        d = deg[r0:r1]
+        k = pos_d[r0:r1] // community                                    # community of each row (layout space)
+        c_lo = k * community
+        c_sz = torch.clamp(c_lo + community, max=n) - c_lo
+        d_in = torch.minimum(torch.round(d.to(torch.float64) * p_in).to(torch.int64), c_sz)
+        d_in = torch.maximum(d_in, d - (n - c_sz))                       # the rest must fit outside
+        row = torch.repeat_interleave(torch.arange(r1 - r0, device=device), d)
+        j = torch.arange(e0, e1, device=device) - rowptr[r0:r1][row]
+        inside = j < d_in[row]
+        # stratified sample without replacement: d_in strata of the community, d - d_in strata of the complement
+        cnt = torch.where(inside, d_in[row], (d - d_in)[row])
+        span = torch.where(inside, c_sz[row], n - c_sz[row])
+        jj = torch.where(inside, j, j - d_in[row])
+        lo = (jj * span) // cnt
+        hi = ((jj + 1) * span) // cnt
+        u = torch.rand(e1 - e0, generator=gen, device=device, dtype=torch.float64)
+        t = lo + torch.clamp((u * (hi - lo).to(torch.float64)).to(torch.int64), max=(hi - lo - 1))
+        lay = torch.where(inside, c_lo[row] + t, torch.where(t < c_lo[row], t, t + c_sz[row]))   # layout position
+        ids = pi_d[lay]
+        # columns ascending inside a row
+        key = row * n + ids
+        col[e0:e1] = torch.sort(key).values - row * n
+    del n_comm
+    return rowptr, col
+
+
 def synthetic_adj(shape: str = "arxiv", seed: int = 0, device: str = "cpu", scale: float = 1.0) -> SparseTensor:
     """A value-less SparseTensor (what ToSparseTensor produces) of a named dataset shape.  `scale` < 1
     shrinks nodes and edges proportionally (tests)."""

@@ -116,16 +116,17 @@ class ShardedSpMM:
     `chunks` > 1 cuts the local row range into that many nnz-balanced sub-blocks, each with its own plan:
     the all-gather of sub-block k (NCCL's stream) then overlaps the SpMM of sub-block k+1 (compute stream).
 
-    `fused=True` (CUDA, CSR, sp_parts == 1) removes the collective altogether: the result lives in a
+    `fused=True` (CUDA, CSR or sorted COO, sp_parts == 1) removes the collective altogether: the result lives in a
     symmetric-memory buffer and the SpMM kernel's epilogue stores every output row straight into every
     peer's copy over NVLink (one multimem.st through the NVSwitch when multicast is available, else one store
-    per peer), bracketed by two device-side barriers.  The transfer overlaps the gathers row by row.
+    per peer); the kernel itself signals completion to the peers (`sync="flags"`), so there is no barrier and no
+    extra launch between two layers beyond a one-warp wait.  The transfer overlaps the gathers row by row.
     """
 
     def __init__(self, adj: Optional[SparseTensor], args, group=None, splits: Optional[Sequence[int]] = None,
                  local_adj: Optional[SparseTensor] = None,
                  make_local: Optional[Callable[[SparseTensor, object], object]] = None, chunks: int = 1,
-                 fused: bool = False, use_multicast: bool = True):
+                 fused: bool = False, use_multicast: bool = True, sync: str = "flags"):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -159,39 +160,61 @@ class ShardedSpMM:
         self.local = self.locals[0]
         self.fused = bool(fused) and self.world > 1
         self.use_multicast = use_multicast
-        self._symm = {}          # dtype -> (buffer, handle)
+        assert sync in ("flags", "barrier")
+        self.sync = sync         # how a fused call learns that every peer's rows have landed
+        self.peer_mask = None    # optional uint8 [local rows]: bit p = peer p needs the row (halo exchange)
+        self._symm = {}          # dtype -> [slots, next slot, flags, flag ptrs, epochs]
         if self.fused and self.chunks != 1:
             raise ValueError("fused=True replaces the chunked NCCL schedule; use chunks=1")
 
     # -- fused all-gather: symmetric result buffer + peer stores from the kernel epilogue
     def _symmetric_out(self, dtype: torch.dtype, device: torch.device):
-        """Two symmetric result buffers per dtype, used alternately."""
+        """Symmetric result buffers per dtype, used in rotation (two with a barrier per call, three with arrival
+        flags), plus - for sync="flags" - one symmetric int32 flag vector [slots x world]."""
         if dtype not in self._symm:
             import torch.distributed._symmetric_memory as symm_mem
             group = self.group if self.group is not None else dist.group.WORLD
-            pair = []
-            for _ in range(2):
+            n_slots = 3 if self.sync == "flags" else 2
+            slots = []
+            for _ in range(n_slots):
                 buf = symm_mem.empty((self.nrows, self.hidden_size), dtype=dtype, device=device)
                 hdl = symm_mem.rendezvous(buf, group.group_name)
                 mc = int(hdl.multicast_ptr) if (self.use_multicast and hdl.has_multicast_support) else 0
-                pair.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs], mc))
-            self._symm[dtype] = [pair, 0]
-            pair[0][1].barrier(channel=0)     # both buffers exist everywhere before the first remote store
+                slots.append((buf, hdl, [int(p) for p in hdl.buffer_ptrs], mc))
+            flags = symm_mem.empty((n_slots * self.world,), dtype=torch.int32, device=device)
+            flags.zero_()
+            fh = symm_mem.rendezvous(flags, group.group_name)
+            torch.cuda.synchronize(device)
+            self._symm[dtype] = [slots, 0, flags, [int(p) for p in fh.buffer_ptrs], [0] * n_slots]
+            slots[0][1].barrier(channel=0)    # buffers and zeroed flags exist everywhere before the first remote store
         return self._symm[dtype]
 
     def _mul_fused(self, B: torch.Tensor) -> torch.Tensor:
-        """SpMM whose epilogue stores this rank's rows into every peer's buffer; ONE barrier per call.
+        """SpMM whose epilogue stores this rank's rows into every peer's buffer.
 
-        Double buffering makes the leading barrier unnecessary: call k writes buffer k%2, whose previous
-        contents (call k-2) every rank finished consuming before it enqueued call k-1 - and every rank passed
-        call k-1's trailing barrier before any rank can start call k.  The returned buffer stays valid until
-        the call after next."""
+        sync="flags" (default): NO collective and no barrier.  The kernel's last warp writes this call's epoch
+        into every peer's flag slot once all of its rows are stored (release, system scope); each rank then
+        enqueues a one-warp wait on its own flag vector.  Three result buffers rotate: call k writes buffer k%3,
+        which peers can only start to overwrite (call k+3) after this rank's kernel k+2 has finished - so a result
+        stays valid until the call after next has been ENQUEUED here.
+        sync="barrier": two buffers and one symmetric-memory barrier per call (the round-1 scheme)."""
         from .backend_pim import pim_ops
         state = self._symmetric_out(B.dtype, B.device)
-        buf, hdl, ptrs, mc = state[0][state[1]]
-        state[1] ^= 1
-        pim_ops.spmm_run_dense_peers(self.locals[0].sp_info_ptr, B, ptrs, mc, self.hidden_size, self.r0)
-        hdl.barrier(channel=0)          # every rank's rows have landed everywhere
+        slots, k = state[0], state[1]
+        buf, hdl, ptrs, mc = slots[k]
+        state[1] = (k + 1) % len(slots)
+        if self.sync == "flags":
+            state[4][k] += 1
+            epoch = state[4][k]
+            off = k * self.world * 4
+            pim_ops.spmm_run_dense_peers(self.locals[0].sp_info_ptr, B, ptrs, mc, self.hidden_size, self.r0,
+                                         peer_mask=self.peer_mask, flag_ptrs=[p + off for p in state[3]],
+                                         my_rank=self.rank, epoch=epoch)
+            pim_ops.wait_flags(state[2][k * self.world:(k + 1) * self.world], epoch)
+        else:
+            pim_ops.spmm_run_dense_peers(self.locals[0].sp_info_ptr, B, ptrs, mc, self.hidden_size, self.r0,
+                                         peer_mask=self.peer_mask)
+            hdl.barrier(channel=0)          # every rank's rows have landed everywhere
         return buf
 
     def _sub_block_views(self, out: torch.Tensor, k: int):

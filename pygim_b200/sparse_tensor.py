@@ -6,7 +6,7 @@ Libs/install_libs.sh:13) that is not installable here.  Only the data-structure 
 backend touches is provided: construction from COO or CSR, ``coo() / csr() / nnz() / sizes() /
 size(d) / sparse_sizes() / device() / int() / to() / t()`` and column slicing ``adj[:, a:b]``.
 There is deliberately NO ``matmul`` here: the CPU SpMM of ``--version=cpu`` is the baseline, it
-lives with the oracle (oracle/torch_sparse_cpu.py), not in the product.
+lives with the oracle (oracle/spmm_oracle.c::oracle_spmm_csr_rowpar_*), not in the product.
 
 A real ``torch_sparse.SparseTensor`` works with pygim_b200.backend_pim too (duck typing).
 """

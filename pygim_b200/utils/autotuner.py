@@ -148,8 +148,8 @@ def default_space(hidden: int) -> Space:
     return For("sp_parts", [1, 2, 4]) * For("ds_parts", [d for d in (1, 2, 4, 8) if hidden % d == 0])
 
 
-def autotune(adj_or_stats, hidden_size: int, split_set: Optional[Sequence[Tuple[int, int]]] = None,
-             blnc_set: Sequence[int] = (0, 2), elem_size: int = 4, fmt: str = "CSR",
+def autotune(adj_or_stats, hidden_size, split_set=None,
+             blnc_set: Sequence = (0, 2), elem_size: int = 4, fmt: str = "CSR",
              dev: Optional[DeviceModel] = None) -> List:
     """Returns `[sp_parts, ds_parts, balance, balance_tsklt, extra]` like the reference (utils/autotuner.py:338).
 
@@ -158,7 +158,14 @@ def autotune(adj_or_stats, hidden_size: int, split_set: Optional[Sequence[Tuple[
     nnz-based (long rows are cut into segments, work is ticketed), so `balance`/`balance_tsklt` are "nnz" unless
     the graph has no skew at all, where plain row tickets ("row") suffice.  `extra` carries the scheduling
     parameters and the predicted time."""
-    if isinstance(adj_or_stats, GraphStats):
+    if isinstance(adj_or_stats, str):
+        # the reference's positional form: autotune(datadir, dataset, hidden_size, split_set, blnc_set)
+        # (utils/autotuner.py:263; called as autotune(data_root, dataset, dense_size, sp_ds_set) at
+        # utils/experiment.py:400)
+        datadir, dataset, hidden_size = adj_or_stats, hidden_size, split_set
+        split_set = blnc_set if blnc_set and isinstance(blnc_set[0], (tuple, list)) else None
+        stats = load_dataset_stats(datadir, str(dataset))
+    elif isinstance(adj_or_stats, GraphStats):
         stats = adj_or_stats
     else:
         stats = GraphStats.from_rowptr(adj_or_stats.csr()[0], adj_or_stats.size(1))
@@ -177,5 +184,156 @@ def autotune(adj_or_stats, hidden_size: int, split_set: Optional[Sequence[Tuple[
     balance = "nnz" if skewed else "row"
     extra = {"predicted_ms": best_ms, "seg_len": seg_len,
              "rows_per_ticket": int(max(1, min(31, 256 // max(1.0, stats.mean_degree)))),
-             "kernel": "coo-segmented" if fmt == "COO" else "csr-ticketed"}
+             "options": kernel_options(stats, hidden_size, elem_size),
+             "kernel": "csr-streamed-rows" if stats.mean_degree < 96 else "csr-row-per-warp+segments"}
     return [best["sp_parts"], best["ds_parts"], balance, "nnz", extra]
+
+
+# ====================================================================================== plan tuning (in the loop)
+# The reference consumes autotune() where the experiment is assembled (utils/experiment.py:398-401: the tuned
+# [sp_parts, ds_parts, balance, balance_tsklt] become the CLI of the run).  Here the consumer is
+# prepare_pim_spmm(..., args.tune / ds_parts == 0): the pick becomes the plan's column tiling and its kernel
+# options, and is persisted next to the dataset so the next run skips the search.
+TUNE_FILE = "pygim_b200_tune.json"
+
+
+def kernel_options(stats: GraphStats, hidden: int, elem_size: int, reordered: bool = False) -> Dict[str, int]:
+    """Kernel variant + scheduling options (pygim_plan_set_option keys) from degree skew, nnz/row and row bytes."""
+    opts: Dict[str, int] = {}
+    short = stats.mean_degree < 96
+    opts["short_rows"] = 2 if short else 0          # streamed row items vs deep-unrolled per-row gathers
+    # work items: ~256 nonzeros; very short rows are capped by the 31-row limit, so aim lower to keep items even
+    opts["item_nnz"] = 256 if stats.mean_degree >= 8 else 128
+    if reordered:
+        # rows that share neighbours are adjacent: let an SM's warps share one superticket's working set, and keep
+        # a gathered chunk to one 128-byte L1 line per dense row so the community's rows fit the L1
+        if hidden * elem_size > 128 and not short:
+            opts["max_g"] = 8
+    return opts
+
+
+def candidate_options(stats: GraphStats, hidden: int, elem_size: int, reordered: bool = False) -> List[Dict[str, int]]:
+    """The (small) space a measured search walks: the analytic pick first, then its neighbours."""
+    base = kernel_options(stats, hidden, elem_size, reordered)
+    out = [dict(base)]
+    for sr in (0, 2):
+        if sr != base["short_rows"]:
+            out.append({**base, "short_rows": sr})
+    for item in (128, 512):
+        if item != base["item_nnz"]:
+            out.append({**base, "item_nnz": item})
+    if hidden * elem_size > 128:
+        out.append({**base, "max_g": 8} if "max_g" not in base else {k: v for k, v in base.items() if k != "max_g"})
+    out.append({**base, "cta_threads": 1024})
+    return out
+
+
+def _graph_key(stats: GraphStats, hidden: int, dtype, fmt: str, reordered: bool, dataset: Optional[str]) -> str:
+    name = dataset or "graph"
+    return "%s|n=%d|m=%d|nnz=%d|maxdeg=%d|H=%d|%s|%s|reord=%d" % (
+        name, stats.nrows, stats.ncols, stats.nnz, stats.max_degree, hidden, str(dtype).replace("torch.", ""), fmt,
+        int(reordered))
+
+
+def _load_cache(cache_dir: Optional[str]) -> dict:
+    if not cache_dir:
+        return {}
+    try:
+        with open(os.path.join(cache_dir, TUNE_FILE)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def _store_cache(cache_dir: Optional[str], cache: dict) -> None:
+    if not cache_dir:
+        return
+    try:
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = os.path.join(cache_dir, TUNE_FILE + ".tmp")
+        with open(tmp, "w") as f:
+            json.dump(cache, f, indent=1, sort_keys=True)
+        os.replace(tmp, os.path.join(cache_dir, TUNE_FILE))
+    except OSError:
+        pass
+
+
+def measure_options(A, x, candidates: Sequence[Dict[str, int]], repeats: int = 5) -> List[float]:
+    """Median CUDA-event time (ms) of A.mul(x) under each option set; the plan's options are restored to automatic."""
+    import torch
+    from ..backend_pim import pim_ops
+    keys = sorted({k for c in candidates for k in c})
+    times = []
+    for cand in candidates:
+        for k in keys:
+            pim_ops.plan_set_option(A.sp_info_ptr, k, cand.get(k, -1))
+        A.mul(x)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(repeats):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            A.mul(x)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        times.append(sorted(ts)[len(ts) // 2])
+    for k in keys:
+        pim_ops.plan_set_option(A.sp_info_ptr, k, -1)
+    return times
+
+
+def tune_plan(adj, hidden_size: int, dtype=None, fmt: str = "CSR", cache_dir: Optional[str] = None,
+              dataset: Optional[str] = None, reordered: bool = False, dev: Optional[DeviceModel] = None) -> dict:
+    """{"sp_parts", "ds_parts", "options", "predicted_ms", "source"} for one plan; persisted in
+    `cache_dir/pygim_b200_tune.json` (the reference keeps its tuning inputs next to --datadir as well,
+    utils/autotuner.py:386-419)."""
+    import torch
+    elem = torch.empty((), dtype=dtype or torch.float32).element_size()
+    stats = adj if isinstance(adj, GraphStats) else GraphStats.from_rowptr(adj.csr()[0], adj.size(1))
+    key = _graph_key(stats, hidden_size, dtype, fmt, reordered, dataset)
+    cache = _load_cache(cache_dir)
+    if key in cache:
+        hit = dict(cache[key])
+        hit["source"] = "cache"
+        return hit
+    if dev is None:
+        info = None
+        try:
+            from ..backend_pim import pim_ops
+            info = pim_ops.device_info()
+        except Exception:
+            pass
+        dev = DeviceModel.from_environment(info)
+    ds = choose_ds_parts(stats.ncols, hidden_size, elem, dev.l2_bytes, dev.l2_resident_fraction)
+    choice = {"sp_parts": 1, "ds_parts": ds, "options": kernel_options(stats, hidden_size, elem, reordered),
+              "predicted_ms": predict_ms(stats, hidden_size, elem, 1, ds, dev, fmt), "source": "model"}
+    cache[key] = {k: v for k, v in choice.items() if k != "source"}
+    _store_cache(cache_dir, cache)
+    return choice
+
+
+def load_dataset_stats(datadir: str, dataset: str) -> GraphStats:
+    """Graph statistics of a dataset directory as the reference's tuner reads it (utils/autotuner.py:386-419 loads
+    `<datadir>/<dataset>` through PyG).  No dataset can be downloaded here: a `<dataset>.pt` / `<dataset>.npz` file
+    holding rowptr (and ncols) is read if present, else the named synthetic shape is used."""
+    import torch
+    base = os.path.join(datadir, dataset)
+    for ext in (".pt", ".npz"):
+        if os.path.exists(base + ext):
+            if ext == ".pt":
+                blob = torch.load(base + ext)
+                return GraphStats.from_rowptr(blob["rowptr"], int(blob.get("ncols", blob["rowptr"].numel() - 1)))
+            import numpy as np
+            blob = np.load(base + ext)
+            return GraphStats.from_rowptr(torch.from_numpy(blob["rowptr"]), int(blob["ncols"]) if "ncols" in blob else None)
+    from .. import graphgen
+    shape = {"ogbn-arxiv": "arxiv", "Reddit": "reddit", "reddit": "reddit", "ogbn-products": "products",
+             "PubMed": "pubmed"}.get(dataset, dataset)
+    if shape not in graphgen.SHAPES:
+        raise FileNotFoundError("no %s.pt/.npz under %s and no synthetic shape of that name" % (dataset, datadir))
+    n, nnz, max_deg = graphgen.SHAPES[shape]
+    deg = graphgen.degree_sequence(n, nnz, max_deg, n, seed=0)
+    rp = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(deg, 0, out=rp[1:])
+    return GraphStats.from_rowptr(rp, n)

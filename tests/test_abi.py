@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", path], stdout=subprocess.PIPE, text=True).stdout
     exported = sorted(set(re.findall(r" T (pygim_\w+)", out)))
     assert exported == _header_symbols()          # nothing undeclared leaks out either
-    assert lib.pygim_abi_version() == 1
+    assert lib.pygim_abi_version() == 2
 
 
 def test_signatures_are_plain_c():

@@ -29,9 +29,10 @@ def _worker(rank, world, port, ret):
             x = graphgen.reference_features(n, hidden, dtype, seed=1)
             args = types.SimpleNamespace(data_type=dtype, sp_format="CSR", hidden_size=hidden, sp_parts=1, ds_parts=1)
             want = O.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None, x.numpy())
-            for kw in (dict(chunks=1), dict(chunks=3), dict(fused=True, use_multicast=False), dict(fused=True)):
+            for kw in (dict(chunks=1), dict(chunks=3), dict(fused=True, use_multicast=False), dict(fused=True),
+                       dict(fused=True, sync="barrier"), dict(fused=True, sync="flags", use_multicast=False)):
                 op = ShardedSpMM(adj.to("cuda"), args, **kw)
-                for _ in range(3):
+                for _ in range(5):            # more calls than rotating buffers
                     out = op.mul(x.cuda())
                 torch.cuda.synchronize()
                 good = bool(np.array_equal(out.cpu().numpy(), want))
