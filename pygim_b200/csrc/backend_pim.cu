@@ -109,8 +109,7 @@ static int context_init(int device) {
 struct CsrPlan {
     long long row_begin = 0, row_end = 0;
     Seg *d_segs = nullptr;
-    int2 *d_items = nullptr;
-    int *d_super_ptr = nullptr;
+    int4 *d_supers = nullptr;
     int *d_long_rows = nullptr;
     int *d_long_seg_ptr = nullptr;
     int n_items = 0, n_super = 0;
@@ -193,8 +192,7 @@ static int auto_seg_len(const SparsePart &p) {
 
 static void free_plan(CsrPlan &c) {
     if (c.d_segs) cudaFree(c.d_segs);
-    if (c.d_items) cudaFree(c.d_items);
-    if (c.d_super_ptr) cudaFree(c.d_super_ptr);
+    if (c.d_supers) cudaFree(c.d_supers);
     if (c.d_long_rows) cudaFree(c.d_long_rows);
     if (c.d_long_seg_ptr) cudaFree(c.d_long_seg_ptr);
     c = CsrPlan();
@@ -214,38 +212,27 @@ template <typename V> static int upload(V **dst, const std::vector<V> &src) {
     return PYGIM_OK;
 }
 
-// Work items of the rows [r0, r1), in row order.  A row longer than seg_len becomes ceil(nnz/seg_len) near-equal
-// segments (their partial sums are merged in the kernel); shorter rows are grouped, item_nnz nonzeros or item_rows
-// rows per item, whichever comes first.  Row ids are relative to r0 (the kernel is handed rowptr + r0), nonzero
-// offsets stay absolute.  Items are then bundled into supertickets of about super_nnz nonzeros.
+// Supertickets of the rows [r0, r1).  A row longer than seg_len becomes ceil(nnz/seg_len) near-equal segments (their
+// partial sums are merged in the kernel); the segments form the first supertickets, longest first.  The rows
+// themselves are cut, in row order, into supertickets of about super_nnz nonzeros; inside one the rows are dealt
+// `rows_per_item` at a time (about item_nnz nonzeros, at most 31 rows) - an item's rows follow from its ticket by
+// arithmetic, no descriptor load.  Row ids are relative to r0 (the kernel is handed rowptr + r0), nonzero offsets
+// stay absolute.
 static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, long long r0, long long r1, CsrPlan &out) {
     free_plan(out);
     out.row_begin = r0;
     out.row_end = r1;
     std::vector<Seg> segs;
-    std::vector<int2> items;
-    std::vector<long long> item_nnz;          // nonzeros per item (for the superticket cut)
     std::vector<int> long_rows, long_ptr;
     long_ptr.push_back(0);
     const std::vector<int> &rp = p.h_rowptr;
-    const long long mean = p.nrows > 0 ? p.nnz / std::max<long long>(p.nrows, 1) : 0;
     const long long target = g.opt_item_nnz > 0 ? g.opt_item_nnz : 256;
     const int max_rows = (int)std::max<long long>(1, std::min<long long>(31, g.opt_rows_per_ticket > 0 ? g.opt_rows_per_ticket : 31));
-    (void)mean;
-    int cur_first = -1, cur_cnt = 0;
-    long long cur_nnz = 0;
-    auto flush = [&]() {
-        if (cur_cnt > 0) {
-            items.push_back(make_int2(cur_first, cur_cnt));
-            item_nnz.push_back(cur_nnz);
-        }
-        cur_first = -1; cur_cnt = 0; cur_nnz = 0;
-    };
+    long long short_nnz = 0;
     for (long long r = r0; r < r1; ++r) {
         const long long s = (unsigned)rp[r], e = (unsigned)rp[r + 1];
         const long long n = e - s;
         if (n > seg_len) {
-            flush();
             const long long k = (n + seg_len - 1) / seg_len;
             // equal pieces rounded up to a multiple of 32 so every piece but the last runs full rounds
             const long long piece = ((n + k - 1) / k + 31) / 32 * 32;
@@ -255,42 +242,59 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
                 sg.start = (int)b;
                 sg.end = (int)std::min(e, b + piece);
                 sg.slot = (int)segs.size();
-                items.push_back(make_int2(~(int)segs.size(), 0));
-                item_nnz.push_back(sg.end - sg.start);
                 segs.push_back(sg);
             }
             long_rows.push_back((int)(r - r0));
             long_ptr.push_back((int)segs.size());
         } else {
-            if (cur_cnt > 0 && (cur_nnz + n > target || cur_cnt >= max_rows)) flush();
-            if (cur_cnt == 0) cur_first = (int)(r - r0);
-            ++cur_cnt;
-            cur_nnz += n;
+            short_nnz += n;
         }
     }
-    flush();
-    // supertickets: ~16 per SM, at least 2048 nonzeros (small graphs) and at most 128 K
-    long long total = 0;
-    for (long long v : item_nnz) total += v;
-    long long super = g.opt_super_nnz > 0 ? g.opt_super_nnz
-                                          : std::min<long long>(131072, std::max<long long>(2048, total / std::max(1, g_ctx.sm_count * 16)));
-    std::vector<int> super_ptr;
-    super_ptr.push_back(0);
-    long long acc = 0;
-    for (size_t k = 0; k < items.size(); ++k) {
-        acc += std::max<long long>(item_nnz[k], 1);
-        if (acc >= super || k + 1 == items.size()) {
-            super_ptr.push_back((int)k + 1);
-            acc = 0;
+    long long seg_nnz = 0;
+    for (const Seg &sg : segs) seg_nnz += sg.end - sg.start;
+    // ~16 supertickets per SM, at least 2048 nonzeros (small graphs) and at most 128 K
+    const long long super = g.opt_super_nnz > 0 ? g.opt_super_nnz
+                                                : std::min<long long>(131072, std::max<long long>(2048, (short_nnz + seg_nnz) / std::max(1, g_ctx.sm_count * 16)));
+    std::vector<int4> supers;
+    long long n_items = 0;
+    if (!segs.empty()) {
+        // longest pieces first: tickets are handed out in index order (slots keep the row order for the merge)
+        std::stable_sort(segs.begin(), segs.end(),
+                         [](const Seg &x, const Seg &y) { return (x.end - x.start) > (y.end - y.start); });
+        long long acc = 0;
+        int first = 0;
+        for (size_t k = 0; k < segs.size(); ++k) {
+            acc += segs[k].end - segs[k].start;
+            if (acc >= super || k + 1 == segs.size()) {
+                supers.push_back(make_int4(~first, 0, 0, (int)k + 1 - first));
+                n_items += (long long)k + 1 - first;
+                first = (int)k + 1;
+                acc = 0;
+            }
         }
     }
-    out.n_items = (int)items.size();
-    out.n_super = (int)super_ptr.size() - 1;
+    {
+        long long acc = 0, first = r0;
+        for (long long r = r0; r < r1; ++r) {
+            const long long n = (long long)(unsigned)rp[r + 1] - (long long)(unsigned)rp[r];
+            acc += n > seg_len ? 0 : std::max<long long>(n, 1);
+            if (acc >= super || r + 1 == r1) {
+                const long long rows = r + 1 - first;
+                const long long per = std::max<long long>(1, std::min<long long>(max_rows, (target * rows + acc / 2) / std::max<long long>(acc, 1)));
+                const long long items = (rows + per - 1) / per;
+                supers.push_back(make_int4((int)(first - r0), (int)rows, (int)per, (int)items));
+                n_items += items;
+                first = r + 1;
+                acc = 0;
+            }
+        }
+    }
+    out.n_items = (int)std::min<long long>(n_items, 0x7fffffff);
+    out.n_super = (int)supers.size();
     out.n_seg = (int)segs.size();
     out.n_long = (int)long_rows.size();
     int rc;
-    if ((rc = upload(&out.d_items, items))) return rc;
-    if (out.n_items > 0 && (rc = upload(&out.d_super_ptr, super_ptr))) return rc;
+    if ((rc = upload(&out.d_supers, supers))) return rc;
     if (out.n_seg > 0) {
         if ((rc = upload(&out.d_segs, segs)) || (rc = upload(&out.d_long_rows, long_rows)) ||
             (rc = upload(&out.d_long_seg_ptr, long_ptr)))
@@ -509,11 +513,10 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.colind = p.colind;
         l.val = p.values;
         l.B = B;
-        l.C = C;
+        l.C = C + (size_t)pl.row_begin * (size_t)ldc * (float_out ? sizeof(float) : s);
         l.partial = sc->partial;
         l.segs = pl.d_segs;
-        l.items = pl.d_items;
-        l.super_ptr = pl.d_super_ptr;
+        l.supers = pl.d_supers;
         l.long_rows = pl.d_long_rows;
         l.long_seg_ptr = pl.d_long_seg_ptr;
         l.warps_out = reinterpret_cast<unsigned int *>(sc->counters);
@@ -524,6 +527,7 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.n_seg = pl.n_seg;
         l.n_long = pl.n_long;
         l.nrows = (int)(pl.row_end - pl.row_begin);
+        l.seg_len = p.seg_len;
         l.nnz_total = p.nnz;
         l.short_rows = g->opt_short_rows >= 0 ? (int)g->opt_short_rows
                                               : (p.nnz < 96 * std::max<long long>(p.nrows, 1) ? 2 : 0);

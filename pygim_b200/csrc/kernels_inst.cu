@@ -20,13 +20,16 @@ using T = PYGIM_T;
 //   THREADS    upper bound of the block size the launcher may pick (bounds the register allocation)
 //   MIN_BLOCKS resident blocks of THREADS threads per SM the register allocation must allow
 #ifndef PYGIM_CSR_NV
-#define PYGIM_CSR_NV 2
+#define PYGIM_CSR_NV 2      // 0 = the shuffle-delivered index stream of round 1 (csr_accumulate_shfl)
+#endif
+#ifndef PYGIM_CSR_NV_WEIGHTED
+#define PYGIM_CSR_NV_WEIGHTED 1
 #endif
 // default: 64 registers (one 1024-thread block, or four 256-thread blocks, per SM).  8/16-bit types carry
 // E = 16/8 32-bit accumulators per lane: 128 registers, four gathers in flight.  Weighted (non-unit) kernels
 // also hold the values of the nonzeros in flight: four gathers.
 template <int E, bool UNIT> struct CsrTune {
-    static constexpr int NV = (E >= 8 || !UNIT) ? 1 : PYGIM_CSR_NV;
+    static constexpr int NV = PYGIM_CSR_NV == 0 ? 0 : ((E >= 8 || !UNIT) ? PYGIM_CSR_NV_WEIGHTED : PYGIM_CSR_NV);
     static constexpr int THREADS = (E >= 8) ? 512 : 1024;
     static constexpr int MIN_BLOCKS = 1;
 };
@@ -34,9 +37,16 @@ template <int E, bool UNIT> struct CsrTune {
 // row (index load -> gather -> shuffle tree -> store), not by gathers in flight: more resident warps win
 // (measured on products-shape: H=16 1.66 -> 0.93 ms, H=32 1.93 -> 1.34 ms, H=64 2.92 -> 2.36 ms).
 template <int E, bool UNIT> struct CsrTuneShort {
-    static constexpr int NV = 1;
+    static constexpr int NV = PYGIM_CSR_NV == 0 ? 0 : 1;
     static constexpr int THREADS = 256;
     static constexpr int MIN_BLOCKS = (E >= 8) ? 2 : 6;
+};
+// Streamed row items (short_rows == 2): the row path is csr_stream_rows; the segment path keeps four gathers in
+// flight so the two code paths share one 64-register budget
+template <int E, bool UNIT> struct CsrTuneStream {
+    static constexpr int NV = PYGIM_CSR_NV == 0 ? 0 : 1;
+    static constexpr int THREADS = (E >= 8) ? 512 : 1024;
+    static constexpr int MIN_BLOCKS = 1;
 };
 // COO carries a third index stream and the run walker: one block less per SM than CSR keeps it spill-free
 #ifndef PYGIM_CSR_UNROLL
@@ -81,7 +91,7 @@ static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t
     // the 16-byte-word instantiations of 32/64-bit types come in two register budgets (see CsrTuneShort)
     // (rows of 512 bytes and more - G == 32 - gain nothing from either: measured 5.11 vs 4.97 ms on products-shape)
     if constexpr (E < 8 && sizeof(T) * E >= 16 && G < 32) {
-        if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>, true>(a, l, launches);   // streamed
+        if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTuneStream<E, UNIT>, true>(a, l, launches);   // streamed
         if (l.short_rows) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, UNIT>>(a, l, launches);
     }
     return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>>(a, l, launches);
@@ -96,8 +106,7 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.C = l.C;
     a.partial = static_cast<T *>(l.partial);
     a.segs = l.segs;
-    a.items = l.items;
-    a.super_ptr = l.super_ptr;
+    a.supers = l.supers;
     a.long_rows = l.long_rows;
     a.long_seg_ptr = l.long_seg_ptr;
     a.super_cnt = l.super_cnt;
@@ -107,6 +116,7 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     a.n_long = l.n_long;
     a.n_seg = l.n_seg;
     a.nrows = l.nrows;
+    a.seg_len = l.seg_len;
     a.nvec = (int)(l.ncols / E);
     a.nnz_total = l.nnz_total;
     {   // vector index loads need colind and val misaligned by the same number of ELEMENTS (mod 4)

@@ -32,14 +32,13 @@ struct CsrLaunch {
     void *C;                  // element type of the plan, or float32 when epi.scale / epi.residual is set
     void *partial;            // scratch [n_seg x ldp]
     const Seg *segs;
-    const int2 *items;        // work items in row order (x >= 0: rows [x, x+y); x < 0: segment ~x)
-    const int *super_ptr;     // [n_super + 1] item ranges of the supertickets
+    const int4 *supers;       // [n_super] supertickets (x >= 0: rows [x, x+y), z rows per item, w items; x < 0: w segments from ~x)
     const int *long_rows;
     const int *long_seg_ptr;
     int *super_cnt;           // [n_super x col_chunks] zeroed draw counters
     int *seg_count;           // [col_chunks x n_long] zeroed arrival counters of the long rows
     unsigned int *warps_out;  // zeroed
-    int n_super, n_items, n_seg, n_long, nrows;
+    int n_super, n_items, n_seg, n_long, nrows, seg_len;
     long long nnz_total;
     int short_rows;           // mean degree is small: 1 = high-occupancy instantiation, 2 = + streamed row items
     int max_g;                // lanes per dense row are capped at this power of two (column chunks beyond it)

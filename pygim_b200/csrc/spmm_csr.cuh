@@ -75,8 +75,8 @@ template <typename T> struct CsrArgs {
     void *C;           // output (T, or float when epi.scale is set), row stride ldc elements
     T *partial;        // [n_seg x ldp] scratch for segment items (ldp covers the whole dense row)
     const Seg *segs;
-    const int2 *items;          // x >= 0: rows [x, x + y);  x < 0: segment ~x
-    const int *super_ptr;       // [n_super + 1] items of superticket s are [ptr[s], ptr[s+1])
+    const int4 *supers;         // [n_super] supertickets.  x >= 0: rows [x, x + y) dealt z rows per item (w items);
+                                //            x < 0: the w segments ~x, ~x + 1, ... of long rows
     const int *long_rows;       // [n_long] row id of every long row
     const int *long_seg_ptr;    // [n_long + 1] slots of long row i are [ptr[i], ptr[i+1])
     int *super_cnt;             // [n_super x col_chunks] items drawn per (superticket, column chunk); zero at rest
@@ -85,6 +85,7 @@ template <typename T> struct CsrArgs {
     unsigned int n_warps;       // warps of this launch
     int n_super, n_seg, n_long;
     int nrows;
+    int seg_len;       // rows with more nonzeros than this are covered by segments (row items skip them)
     int nvec;          // words (of E elements) per dense row
     int col_chunks;    // ceil(nvec / G): every item is processed once per chunk of G words
     long long nnz_total;        // entries of colind/val (bounds of the vector index loads)
@@ -348,6 +349,95 @@ __device__ __forceinline__ void csr_accumulate(const CsrArgs<T> &a, int start, i
     }
 }
 
+// Alternative index delivery (the round-1 loop, kept selectable: -DPYGIM_IDX_SHFL=1 or NV == 0): the warp reads
+// 32*R column ids + values per coalesced evict-first load, D batches ahead, and hands them round by shuffles.
+template <typename T, int E, int G, int UNROLL, int R, int D, bool UNIT>
+__device__ __forceinline__ void csr_accumulate_shfl(const CsrArgs<T> &a, int range_start, int range_end, const T *Bcol,
+                                                    bool active, typename Arith<T>::Acc (&acc)[E]) {
+    using Shfl = typename Arith<T>::Shfl;
+    constexpr int P = 32 / G;
+    constexpr int BATCH = 32 * R;
+    constexpr int STEPS = G * R;                 // gather steps per full batch (P nonzeros each)
+    constexpr int U = (UNROLL < STEPS) ? UNROLL : STEPS;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int end = range_end;
+    int nc[D][R];
+    Shfl nv[D][R];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = range_start + d * BATCH + r * 32 + lane;
+            nc[d][r] = 0;
+            nv[d][r] = 0;
+            if (i < end) {
+                nc[d][r] = ld_stream(a.colind + i);
+                if constexpr (!UNIT) nv[d][r] = ld_stream(a.val + i);
+            }
+        }
+    }
+    for (int base = range_start; base < end; base += BATCH) {
+        int c[R];
+        Shfl v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { c[r] = nc[0][r]; v[r] = nv[0][r]; }
+#pragma unroll
+        for (int d = 0; d + 1 < D; ++d) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) { nc[d][r] = nc[d + 1][r]; nv[d][r] = nv[d + 1][r]; }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = base + D * BATCH + r * 32 + lane;
+            nc[D - 1][r] = 0;
+            nv[D - 1][r] = 0;
+            if (i < end) {
+                nc[D - 1][r] = ld_stream(a.colind + i);
+                if constexpr (!UNIT) nv[D - 1][r] = ld_stream(a.val + i);
+            }
+        }
+        const int rem = end - base;
+        if (rem >= BATCH) {
+#pragma unroll
+            for (int s0 = 0; s0 < STEPS; s0 += U) {
+                Pack<T, E> b[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int cc = __shfl_sync(FULL, c[(s0 + u) / G], ((s0 + u) % G) * P + sub);
+                    if (active) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    Shfl vv = (Shfl)1;
+                    if constexpr (!UNIT) vv = __shfl_sync(FULL, v[(s0 + u) / G], ((s0 + u) % G) * P + sub);
+                    if (active) fma_pack<T, E>(acc, b[u], vv);
+                }
+            }
+        } else {
+            // tail batch: per-lane predicate so padded slots never touch B (0 * inf would poison a row)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int left = rem - r * 32;          // entries of register r that are real
+                if (left > 0) {
+                    const int steps = (min(left, 32) + P - 1) / P;
+                    for (int s = 0; s < steps; ++s) {
+                        const int src = s * P + sub;
+                        const int cc = __shfl_sync(FULL, c[r], src);
+                        Shfl vv = (Shfl)1;
+                        if constexpr (!UNIT) vv = __shfl_sync(FULL, v[r], src);
+                        if (active && src < left) {
+                            Pack<T, E> b = ld_dense<T, E>(row_ptr<T>(Bcol, cc, a.ldb_bytes));
+                            fma_pack<T, E>(acc, b, vv);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // One row (or one segment of a long row): accumulate, combine the lane groups, store / publish.
 template <typename T, int E, int G, int NV, bool UNIT>
 __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range_start, int range_end, int chunk,
@@ -364,7 +454,13 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
     Acc acc[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
-    csr_accumulate<T, E, G, NV, UNIT>(a, range_start, range_end, Bcol, active, acc);
+    if constexpr (NV > 0) {
+        csr_accumulate<T, E, G, NV, UNIT>(a, range_start, range_end, Bcol, active, acc);
+    } else {
+        constexpr int UNROLL = (E >= 8) ? 4 : 8;
+        constexpr int R = (G >= UNROLL) ? 1 : ((UNROLL / G) > 4 ? 4 : (UNROLL / G));
+        csr_accumulate_shfl<T, E, G, UNROLL, R, (R > 1) ? 1 : 2, UNIT>(a, range_start, range_end, Bcol, active, acc);
+    }
 
     if (long_idx >= 0) {
 #pragma unroll
@@ -474,21 +570,22 @@ struct CsrItem {
     int rp;            // rows: lane l holds rowptr[first + l] (l <= count); segment: lane 0 start, other lanes end
 };
 
-template <typename T> __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, int idx) {
+// Item `it` of superticket `sp`.  Its address follows from the ticket by arithmetic alone: ONE dependent load
+// (rowptr entries, or the segment descriptor) between drawing a ticket and having the item.
+template <typename T> __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, const int4 &sp, int it) {
     CsrItem r;
     const int lane = threadIdx.x & 31;
-    const int2 it = __ldg(a.items + idx);
-    if (it.x < 0) {
-        const Seg sg = a.segs[~it.x];
+    if (sp.x < 0) {
+        const Seg sg = a.segs[~sp.x + it];
         r.long_idx = sg.long_idx;
         r.first = sg.slot;
         r.count = 1;
         r.rp = lane == 0 ? sg.start : sg.end;
     } else {
         r.long_idx = -1;
-        r.first = it.x;
-        r.count = it.y;
-        r.rp = a.rowptr[min(it.x + lane, a.nrows)];
+        r.first = sp.x + it * sp.z;
+        r.count = min(sp.z, sp.x + sp.y - r.first);
+        r.rp = a.rowptr[min(r.first + lane, a.nrows)];
     }
     return r;
 }
@@ -529,7 +626,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
 
     auto process = [&](const CsrItem &cur, int chunk) {
         if (STREAM && cur.long_idx < 0) {
-            csr_stream_rows<T, E, G, 4, 2, UNIT>(a, cur.first, 0, cur.count, cur.rp, chunk);
+            // rows longer than seg_len are covered by their segments: stream the row blocks between them
+            const int deg = __shfl_down_sync(FULL, cur.rp, 1) - cur.rp;
+            const unsigned long_rows = __ballot_sync(FULL, lane < cur.count && deg > a.seg_len);
+            int ja = 0;
+            while (ja < cur.count) {
+                const unsigned rest = long_rows >> ja;
+                const int jb = rest ? ja + (__ffs(rest) - 1) : cur.count;
+                if (jb > ja) csr_stream_rows<T, E, G, 4, 2, UNIT>(a, cur.first, ja, jb, cur.rp, chunk);
+                ja = jb + 1;
+            }
         } else if (cur.long_idx >= 0) {
             csr_process_range<T, E, G, NV, UNIT>(a, __shfl_sync(FULL, cur.rp, 0), __shfl_sync(FULL, cur.rp, 1), chunk,
                                                  cur.first, cur.long_idx);
@@ -537,16 +643,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             for (int j = 0; j < cur.count; ++j) {
                 const int start = __shfl_sync(FULL, cur.rp, j);
                 const int end = __shfl_sync(FULL, cur.rp, j + 1);
-                csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.first + j, -1);
+                if (end - start <= a.seg_len)      // longer rows are covered by their segments
+                    csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.first + j, -1);
             }
         }
     };
 
-    // drain one (superticket, chunk): one atomic per item, the next item is drawn (and its descriptor loaded)
-    // before the current one is processed
+    // drain one (superticket, chunk): one atomic per item.  Tickets are drawn TWO items ahead: while item k is
+    // processed, the rowptr / descriptor load of item k+1 (its ticket arrived an item ago) and the atomic of item
+    // k+2 are in flight, so neither latency is on the critical path.
     auto drain = [&](int unit) {
         const int s = unit / a.col_chunks, chunk = unit - s * a.col_chunks;
-        const int lo = a.super_ptr[s], n = a.super_ptr[s + 1] - lo;
+        const int4 sp = __ldg(a.supers + s);
+        const int n = sp.w;
         int *cnt = a.super_cnt + unit;
         auto take = [&]() -> int {
             int t = 0;
@@ -554,41 +663,50 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             return __shfl_sync(FULL, t, 0);
         };
         int it = take();
+        int nit = take();
         CsrItem cur;
-        if (it < n) cur = csr_load_item<T>(a, lo + it);
+        if (it < n) cur = csr_load_item<T>(a, sp, it);
         while (it < n) {
-            const int nit = take();
+            const int nnit = (nit < n) ? take() : n;
             CsrItem nxt;
-            if (nit < n) nxt = csr_load_item<T>(a, lo + nit);
+            if (nit < n) nxt = csr_load_item<T>(a, sp, nit);
             process(cur, chunk);
             it = nit;
+            nit = nnit;
             cur = nxt;
         }
     };
 
-    // home supertickets: keyed by the SM, not by the block, so every block resident on an SM drains the same ones
+    // Home supertickets are keyed by the SM, not by the block, so every block resident on an SM drains the same
+    // ones; when they are exhausted the warp steals from any (superticket, chunk) that still has undrawn items,
+    // scanning the draw counters 32 at a time from an SM-specific offset.
     unsigned smid, nsmid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     asm("mov.u32 %0, %%nsmid;" : "=r"(nsmid));
-    for (int unit = (int)smid; unit < n_units; unit += (int)nsmid) drain(unit);
-    // steal: any (superticket, chunk) that still has undrawn items, scanning from an SM-specific offset
-    {
-        const int base = (int)(((unsigned long long)smid * 2654435761ull) % (unsigned)n_units);
-        for (int o = 0; o < n_units; o += 32) {
-            int u = base + o + lane;
-            if (u >= n_units) u -= n_units;
-            bool open = false;
-            if (o + lane < n_units) {
-                const int s = u / a.col_chunks;
-                open = *(volatile int *)(a.super_cnt + u) < a.super_ptr[s + 1] - a.super_ptr[s];
+    int home = (int)smid, scan_o = 0, scan_u = 0;
+    unsigned scan_m = 0;
+    for (;;) {
+        int unit;
+        if (home < n_units) {
+            unit = home;
+            home += (int)nsmid;
+        } else {
+            while (scan_m == 0 && scan_o < n_units) {
+                const int base = (int)(((unsigned long long)smid * 2654435761ull) % (unsigned)n_units);
+                scan_u = base + scan_o + lane;
+                if (scan_u >= n_units) scan_u -= n_units;
+                bool open = false;
+                if (scan_o + lane < n_units)
+                    open = *(volatile int *)(a.super_cnt + scan_u) < __ldg(&a.supers[scan_u / a.col_chunks].w);
+                scan_m = __ballot_sync(FULL, open);
+                scan_o += 32;
             }
-            unsigned m = __ballot_sync(FULL, open);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                drain(__shfl_sync(FULL, u, src));
-            }
+            if (scan_m == 0) break;
+            const int src = __ffs(scan_m) - 1;
+            scan_m &= scan_m - 1;
+            unit = __shfl_sync(FULL, scan_u, src);
         }
+        drain(unit);
     }
     csr_leave<T>(a);
 }
