@@ -116,8 +116,9 @@ PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle);
  *                    superticket: use with a locality-preserving row order so gathered rows are L1 hits)
  *   max_g            lanes per dense row are capped at this power of two; wider rows run as column chunks of one
  *                    launch (8 = 128-byte chunks, the L1 line)
- *   short_rows       0/1/2 = deep-unroll / high-occupancy / streamed-row-item CSR instantiation (automatic: 2 when
- *                    the mean degree is below 96, else 0)
+ *   short_rows       CSR kernel family: 0 deep (128 registers, 16 gathers per lane in flight), 1 high occupancy
+ *                    (40 registers), 2 streamed row items, 3 light (64 registers, 8 gathers); automatic: 3 when the
+ *                    mean degree is below 96, else 0
  *   unit_values      0 forces the general kernels even when every stored value is one
  *   coo_native       1 runs a sorted COO plan through the COO (segmented reduction) kernel instead of the CSR
  *                    kernels over the derived row pointer

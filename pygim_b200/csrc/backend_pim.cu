@@ -529,8 +529,10 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.nrows = (int)(pl.row_end - pl.row_begin);
         l.seg_len = p.seg_len;
         l.nnz_total = p.nnz;
+        // kernel family: 0 deep (128 registers, 16 gathers in flight) for long rows; 3 light (64 registers, twice the
+        // warps) for short rows; 1 high occupancy and 2 streamed row items stay selectable
         l.short_rows = g->opt_short_rows >= 0 ? (int)g->opt_short_rows
-                                              : (p.nnz < 96 * std::max<long long>(p.nrows, 1) ? 2 : 0);
+                                              : (p.nnz < 96 * std::max<long long>(p.nrows, 1) ? 3 : 0);
         l.max_g = max_g;
         l.cta_threads = g->opt_cta_threads > 0 ? (int)g->opt_cta_threads : 256;
         l.ncols = width;

@@ -17,25 +17,38 @@ using T = PYGIM_T;
 
 // Register budgets / gathers in flight per instantiation family (overridable at build time for experiments).
 //   NV         index vectors (4 nonzeros each) per lane in flight: 4*NV independent gathers before the first FMA
-//   THREADS    upper bound of the block size the launcher may pick (bounds the register allocation)
+//   THREADS    upper bound of the block size the launcher may pick; 65536 / THREADS is the register budget
 //   MIN_BLOCKS resident blocks of THREADS threads per SM the register allocation must allow
+// What decides is whether ptxas can keep ALL 4*NV gathers in flight: with the scheduler state of the persistent
+// kernel live across the loop, 64 registers only fit ~3 (it consumes each gather right after issuing it); measured
+// on Reddit-shape (sweep GFLOP/s): 64 regs NV=2 8500, 85 regs NV=2 8920, 128 regs NV=3 9150, 128 regs NV=4 9290.
 #ifndef PYGIM_CSR_NV
-#define PYGIM_CSR_NV 2      // 0 = the shuffle-delivered index stream of round 1 (csr_accumulate_shfl)
+#define PYGIM_CSR_NV 4      // 0 = the shuffle-delivered index stream of round 1 (csr_accumulate_shfl)
+#endif
+#ifndef PYGIM_CSR_THREADS
+#define PYGIM_CSR_THREADS 512
 #endif
 #ifndef PYGIM_CSR_NV_WEIGHTED
-#define PYGIM_CSR_NV_WEIGHTED 1
+#define PYGIM_CSR_NV_WEIGHTED 2
 #endif
-// default: 64 registers (one 1024-thread block, or four 256-thread blocks, per SM).  8/16-bit types carry
-// E = 16/8 32-bit accumulators per lane: 128 registers, four gathers in flight.  Weighted (non-unit) kernels
-// also hold the values of the nonzeros in flight: four gathers.
+// DEEP (default for long rows): 128 registers, 16 resident warps per SM, 16 gathers per lane in flight.
+// 8/16-bit types carry E = 16/8 32-bit accumulators per lane: four gathers.  Weighted (non-unit) kernels also
+// hold the values of the nonzeros in flight: eight gathers.
 template <int E, bool UNIT> struct CsrTune {
-    static constexpr int NV = PYGIM_CSR_NV == 0 ? 0 : ((E >= 8 || !UNIT) ? PYGIM_CSR_NV_WEIGHTED : PYGIM_CSR_NV);
+    static constexpr int NV = PYGIM_CSR_NV == 0 ? 0 : (E >= 8 ? 1 : (!UNIT ? PYGIM_CSR_NV_WEIGHTED : PYGIM_CSR_NV));
+    static constexpr int THREADS = PYGIM_CSR_THREADS;
+    static constexpr int MIN_BLOCKS = 1;
+};
+// LIGHT (short_rows == 3, default for short rows): 64 registers, 32 resident warps per SM.  Short-row graphs
+// (mean degree < ~100: ogbn-products, citation graphs) are bound by the dependent chain of one row (index load ->
+// gather -> shuffle tree -> store), not by gathers in flight: more resident warps win (products-shape sweep:
+// 2656 GFLOP/s vs 2314 with the deep budget).
+template <int E, bool UNIT> struct CsrTuneLight {
+    static constexpr int NV = PYGIM_CSR_NV == 0 ? 0 : ((E >= 8 || !UNIT) ? 1 : 2);
     static constexpr int THREADS = (E >= 8) ? 512 : 1024;
     static constexpr int MIN_BLOCKS = 1;
 };
-// Short-row graphs (mean degree < ~100: ogbn-products, citation graphs) are bound by the dependent chain of one
-// row (index load -> gather -> shuffle tree -> store), not by gathers in flight: more resident warps win
-// (measured on products-shape: H=16 1.66 -> 0.93 ms, H=32 1.93 -> 1.34 ms, H=64 2.92 -> 2.36 ms).
+// HIGH OCCUPANCY (short_rows == 1): 40 registers, 48 resident warps
 template <int E, bool UNIT> struct CsrTuneShort {
     static constexpr int NV = PYGIM_CSR_NV == 0 ? 0 : 1;
     static constexpr int THREADS = 256;
@@ -68,6 +81,9 @@ static cudaError_t launch_csr_t(CsrArgs<T> a, const CsrLaunch &l, int64_t *launc
     static int blocks_per_sm[33] = {0};   // per instantiation, indexed by warps per block
     int &bps = blocks_per_sm[threads / 32];
     if (bps == 0) {
+        // no shared memory is used: give the whole unified array to the L1 (the gathers' only on-SM reuse)
+        (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        (void)cudaGetLastError();
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, 0);
         if (e != cudaSuccess) return e;
         if (bps < 1) bps = 1;
@@ -92,8 +108,9 @@ static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t
     // (rows of 512 bytes and more - G == 32 - gain nothing from either: measured 5.11 vs 4.97 ms on products-shape)
     if constexpr (E < 8 && sizeof(T) * E >= 16 && G < 32) {
         if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTuneStream<E, UNIT>, true>(a, l, launches);   // streamed
-        if (l.short_rows) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, UNIT>>(a, l, launches);
+        if (l.short_rows == 1) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, UNIT>>(a, l, launches);
     }
+    if (l.short_rows == 3) return launch_csr_t<E, G, UNIT, CsrTuneLight<E, UNIT>>(a, l, launches);
     return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>>(a, l, launches);
 }
 

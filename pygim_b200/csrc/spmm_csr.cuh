@@ -236,12 +236,13 @@ __device__ __noinline__ void csr_finish_long_row(const CsrArgs<T> &a, int chunk,
 // ---------------------------------------------------------------------------------------------- gather loops
 // one nonzero: gather word `vec` of dense row `col` and accumulate
 template <typename T, int E, bool UNIT>
-__device__ __forceinline__ void csr_one(const CsrArgs<T> &a, int i, const T *Bcol, typename Arith<T>::Acc (&acc)[E]) {
+__device__ __forceinline__ void csr_one(const int *colind, const T *val, unsigned ldb_bytes, int i, const T *Bcol,
+                                        typename Arith<T>::Acc (&acc)[E]) {
     using Shfl = typename Arith<T>::Shfl;
-    const int c = __ldg(a.colind + i);
+    const int c = __ldg(colind + i);
     Shfl v = (Shfl)1;
-    if constexpr (!UNIT) v = (Shfl)__ldg(a.val + i);
-    const Pack<T, E> b = ld_dense<T, E>(row_ptr<T>(Bcol, c, a.ldb_bytes));
+    if constexpr (!UNIT) v = (Shfl)__ldg(val + i);
+    const Pack<T, E> b = ld_dense<T, E>(row_ptr<T>(Bcol, c, ldb_bytes));
     fma_pack<T, E>(acc, b, v);
 }
 
@@ -266,87 +267,100 @@ __device__ __forceinline__ void ld_val4(const T *p, typename Arith<T>::Shfl (&v)
 // are in flight: 4*NV independent gathers per lane before the first FMA, and the indices of the following NV words
 // are already loading.
 template <typename T, int E, int G, int NV, bool UNIT>
-__device__ __forceinline__ void csr_accumulate(const CsrArgs<T> &a, int start, int end, const T *Bcol, bool active,
-                                               typename Arith<T>::Acc (&acc)[E]) {
+__device__ __forceinline__ AccPack<T, E> csr_accumulate(const int *colind, const T *val, const T *Bcol, unsigned ldb_bytes,
+                                                        int idx_mis, int start, int end, bool active) {
+    using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
     constexpr int P = 32 / G;
     const int sub = (threadIdx.x & 31) / G;
-    if (!active) return;
-    if (a.idx_mis >= 4) {           // colind / val not co-aligned (foreign views): element by element
-        for (int i = start + sub; i < end; i += P) csr_one<T, E, UNIT>(a, i, Bcol, acc);
-        return;
+    AccPack<T, E> out;
+    Acc (&acc)[E] = out.v;
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+    if (!active) return out;
+    if (idx_mis >= 4) {           // colind / val not co-aligned (foreign views): element by element
+        for (int i = start + sub; i < end; i += P) csr_one<T, E, UNIT>(colind, val, ldb_bytes, i, Bcol, acc);
+        return out;
     }
-    const int mis = a.idx_mis;
+    {   // the row's index (and value) stream comes from HBM: pull it into L2 now, 128 bytes per lane and instruction,
+        // so the vector loads below - issued only NV words ahead of their gathers - find it there
+        const int lane = threadIdx.x & 31;
+        for (int q = start + 32 * lane; q < end; q += 1024) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(colind + q));
+            if constexpr (!UNIT) asm volatile("prefetch.global.L2 [%0];" ::"l"(val + q));
+        }
+    }
+    const int mis = idx_mis;
     const int a0 = min(end, ((start + mis + 3) & ~3) - mis);     // first word boundary >= start
     const int a1 = max(a0, ((end + mis) & ~3) - mis);            // last word boundary <= end
     const int nw = (a1 - a0) >> 2;
-    const int4 *cw = reinterpret_cast<const int4 *>(a.colind + a0);
-    const T *vw = a.val + a0;
+    const int4 *cw = reinterpret_cast<const int4 *>(colind + a0);
+    const T *vw = val + a0;
 
+    // Register budget: the 4*NV gathers in flight (16*NV registers) must not be squeezed out by index storage, so the
+    // index words live in ONE set of registers: as soon as the gathers of a round are issued the registers are
+    // reloaded with the next round's indices - in the shadow of the gather latency (the index stream is an L2 hit
+    // thanks to the prefetch above, so it arrives before the FMAs that wait for the gathers are done).
     int w = sub;
-    int4 nx[NV];
-    Shfl nv[NV][4];
+    int4 c[NV];
+    Shfl v[NV][4];
 #pragma unroll
     for (int n = 0; n < NV; ++n) {
-        nx[n] = make_int4(0, 0, 0, 0);
+        c[n] = make_int4(0, 0, 0, 0);
         if (w + n * P < nw) {
-            nx[n] = __ldcs(cw + w + n * P);
-            if constexpr (!UNIT) ld_val4<T>(vw + 4 * (w + n * P), nv[n]);
+            c[n] = __ldcs(cw + w + n * P);
+            if constexpr (!UNIT) ld_val4<T>(vw + 4 * (w + n * P), v[n]);
         }
     }
     // edges (their latency overlaps the first words' index loads)
     {
         const int nh = a0 - start, ne = nh + (end - a1);
-        for (int e = sub; e < ne; e += P) csr_one<T, E, UNIT>(a, e < nh ? start + e : a1 + (e - nh), Bcol, acc);
+        for (int e = sub; e < ne; e += P) csr_one<T, E, UNIT>(colind, val, ldb_bytes, e < nh ? start + e : a1 + (e - nh), Bcol, acc);
     }
     for (; w + (NV - 1) * P < nw; w += NV * P) {
-        int4 c[NV];
-        Shfl v[NV][4];
+        Pack<T, E> b[NV][4];
+        Shfl vv[NV][4];
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
-            c[n] = nx[n];
+            b[n][0] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].x, ldb_bytes));
+            b[n][1] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].y, ldb_bytes));
+            b[n][2] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].z, ldb_bytes));
+            b[n][3] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].w, ldb_bytes));
             if constexpr (!UNIT) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[n][k] = nv[n][k];
+                for (int k = 0; k < 4; ++k) vv[n][k] = v[n][k];
             }
         }
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
             const int wn = w + (NV + n) * P;
             if (wn < nw) {
-                nx[n] = __ldcs(cw + wn);
-                if constexpr (!UNIT) ld_val4<T>(vw + 4 * wn, nv[n]);
+                c[n] = __ldcs(cw + wn);
+                if constexpr (!UNIT) ld_val4<T>(vw + 4 * wn, v[n]);
             }
         }
-        Pack<T, E> b[NV][4];
-#pragma unroll
-        for (int n = 0; n < NV; ++n) {
-            b[n][0] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].x, a.ldb_bytes));
-            b[n][1] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].y, a.ldb_bytes));
-            b[n][2] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].z, a.ldb_bytes));
-            b[n][3] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].w, a.ldb_bytes));
-        }
 #pragma unroll
         for (int n = 0; n < NV; ++n) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) fma_pack<T, E>(acc, b[n][k], UNIT ? (Shfl)1 : v[n][k]);
+            for (int k = 0; k < 4; ++k) fma_pack<T, E>(acc, b[n][k], UNIT ? (Shfl)1 : vv[n][k]);
         }
     }
     if constexpr (NV > 1) {
-        // fewer than NV words left for this lane group: one at a time (nx[0..] hold them in order)
+        // fewer than NV words left for this lane group: one at a time (c[0..] hold them in order)
 #pragma unroll
         for (int n = 0; n < NV - 1; ++n) {
             if (w + n * P < nw) {
                 Pack<T, E> b[4];
-                b[0] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].x, a.ldb_bytes));
-                b[1] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].y, a.ldb_bytes));
-                b[2] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].z, a.ldb_bytes));
-                b[3] = ld_dense<T, E>(row_ptr<T>(Bcol, nx[n].w, a.ldb_bytes));
+                b[0] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].x, ldb_bytes));
+                b[1] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].y, ldb_bytes));
+                b[2] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].z, ldb_bytes));
+                b[3] = ld_dense<T, E>(row_ptr<T>(Bcol, c[n].w, ldb_bytes));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) fma_pack<T, E>(acc, b[k], UNIT ? (Shfl)1 : nv[n][k]);
+                for (int k = 0; k < 4; ++k) fma_pack<T, E>(acc, b[k], UNIT ? (Shfl)1 : v[n][k]);
             }
         }
     }
+    return out;
 }
 
 // Alternative index delivery (the round-1 loop, kept selectable: -DPYGIM_IDX_SHFL=1 or NV == 0): the warp reads
@@ -455,7 +469,10 @@ __device__ __forceinline__ void csr_process_range(const CsrArgs<T> &a, int range
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
     if constexpr (NV > 0) {
-        csr_accumulate<T, E, G, NV, UNIT>(a, range_start, range_end, Bcol, active, acc);
+        const AccPack<T, E> sum = csr_accumulate<T, E, G, NV, UNIT>(a.colind, a.val, Bcol, a.ldb_bytes, a.idx_mis,
+                                                                     range_start, range_end, active);
+#pragma unroll
+        for (int k = 0; k < E; ++k) acc[k] = sum.v[k];
     } else {
         constexpr int UNROLL = (E >= 8) ? 4 : 8;
         constexpr int R = (G >= UNROLL) ? 1 : ((UNROLL / G) > 4 ? 4 : (UNROLL / G));
@@ -649,30 +666,29 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
         }
     };
 
-    // drain one (superticket, chunk): one atomic per item.  Tickets are drawn TWO items ahead: while item k is
-    // processed, the rowptr / descriptor load of item k+1 (its ticket arrived an item ago) and the atomic of item
-    // k+2 are in flight, so neither latency is on the critical path.
+    // drain one (superticket, chunk): one atomic per item.  The atomic of item k+2 is ISSUED while item k+1's
+    // rowptr / descriptor load is issued and item k is processed; its result is only read an item later, so neither
+    // the L2 atomic nor the dependent load is on the critical path.
     auto drain = [&](int unit) {
         const int s = unit / a.col_chunks, chunk = unit - s * a.col_chunks;
         const int4 sp = __ldg(a.supers + s);
         const int n = sp.w;
         int *cnt = a.super_cnt + unit;
-        auto take = [&]() -> int {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(cnt, 1);
-            return __shfl_sync(FULL, t, 0);
-        };
-        int it = take();
-        int nit = take();
+        int pend = 0;                                   // lane 0: a ticket whose atomic may still be in flight
+        if (lane == 0) pend = atomicAdd(cnt, 1);
+        int it = __shfl_sync(FULL, pend, 0);
+        if (lane == 0) pend = atomicAdd(cnt, 1);
         CsrItem cur;
         if (it < n) cur = csr_load_item<T>(a, sp, it);
         while (it < n) {
-            const int nnit = (nit < n) ? take() : n;
+            const int nit = __shfl_sync(FULL, pend, 0);          // drawn one item ago
             CsrItem nxt;
-            if (nit < n) nxt = csr_load_item<T>(a, sp, nit);
+            if (nit < n) {
+                if (lane == 0) pend = atomicAdd(cnt, 1);         // for the item after next: not awaited here
+                nxt = csr_load_item<T>(a, sp, nit);
+            }
             process(cur, chunk);
             it = nit;
-            nit = nnit;
             cur = nxt;
         }
     };
