@@ -234,17 +234,24 @@ class SweepWorkload:
         self.adj_plain = adj                       # rows in natural order (parity checks read it)
         self.shard_nnz = int(adj.nnz())
         self.reorder_stats = None
-        perm = None
+        perm, hot = None, None
         if reorder:
             from pygim_b200 import reorder as R
             t0 = time.perf_counter()
             adj, perm, self.reorder_stats = R.reorder_rows(adj, reorder)
+            groups = self.reorder_stats.pop("group_of_row", None)
+            if reorder == "tiles":
+                adj, hot = R.hot_cold_plan(adj, groups, hot_k=a.hot_k, super_nnz=a.tile_super_nnz)
+                self.reorder_stats.update(hot_coverage=hot["coverage"], tile_supertickets=hot["supertickets"],
+                                          hot_k=hot["hot_k"], seg_len=hot["seg_len"])
+            del groups
             torch.cuda.synchronize()
             self.reorder_stats["seconds"] = time.perf_counter() - t0
         self.ds_parts = {h: (a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, self.info, self.esize))
                          for h in self.sweep}
         base = SparseTensorCOO(adj, dtype=self.dtype, format=a.format)
         base.row_perm = perm
+        base.hot_plan = hot
         base.build_csr() if a.format == "CSR" else base.build_coo()
         self.plans = {}
         for h in self.sweep:     # one set of int32 CSR/COO arrays shared by the plans (one plan per hidden size)
@@ -731,7 +738,7 @@ def run_sub_workload(a, shape, dev, rank, world, peak, clustered):
     from oracle import oracle as O
     steps, warmup = max(5, min(a.steps, 10)), 3
     rec = {}
-    variants = [("reordered", "cluster"), ("natural_order", None)] if clustered else [("sharded", None)]
+    variants = [("reordered", a.clustered_reorder), ("natural_order", None)] if clustered else [("sharded", None)]
     for name, reorder in variants:
         w = SweepWorkload(a, shape, dev, rank, world, clustered=clustered, reorder=reorder)
         if clustered and reorder:
@@ -880,7 +887,12 @@ def main():
                     help="fused gather: in-kernel arrival flags (no barrier) or one symmetric-memory barrier per call")
     ap.add_argument("--clustered", action="store_true",
                     help="headline graph with block-model communities (same N, nnz, degrees) instead of uniform columns")
-    ap.add_argument("--reorder", default=None, choices=["cluster", "degree"], help="prepare-time row reordering")
+    ap.add_argument("--reorder", default=None, choices=["cluster", "tiles", "degree"],
+                    help="prepare-time row reordering (tiles = cluster + hot/cold shared-memory tiles)")
+    ap.add_argument("--hot-k", type=int, default=1280, help="tile rows of the hot/cold plan")
+    ap.add_argument("--tile-super-nnz", type=int, default=65536, help="nonzeros per superticket of the hot/cold plan")
+    ap.add_argument("--clustered-reorder", default="tiles", choices=["cluster", "tiles"],
+                    help="how the clustered sub-record is reordered")
     ap.add_argument("--opt", action="append", help="plan option key=value (pygim_plan_set_option), repeatable")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "per-call"],
                     help="N = 1 host-operand step: one pipeline over the sweep (spmm_run_dense_many) or four host calls")

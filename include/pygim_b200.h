@@ -174,6 +174,15 @@ PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ld
 PYGIM_API int pygim_spmm_device_peers(pygim_handle_t handle, const void *B, int64_t ldb, void *const *C_peers,
                                       int n_peers, void *C_multicast, int64_t ldc, int64_t row_offset, void *stream);
 
+/* Hot/cold plan for graphs with community structure (csrc/spmm_csr_hc.cuh; built by pygim_b200/reorder.py): the
+ * rows are cut into n_super supertickets at super_rows[0..n_super] (row ids, super_rows[0] = 0, last = nrows); for
+ * superticket k the hot_k columns hot_cols[k * hot_k ...] (-1 = unused) are staged in shared memory while its rows
+ * are processed.  The plan's colind must already be in hot/cold form: the first hot_cnt[r] nonzeros of row r hold
+ * TILE SLOTS (0 .. hot_k-1), the rest column ids; rows longer than the plan's seg_len must be all cold.  Set seg_len
+ * (and other item options) BEFORE this call.  sp_parts == 1. */
+PYGIM_API int pygim_plan_set_hot_tiles(pygim_handle_t handle, int64_t n_super, const int32_t *super_rows, int hot_k,
+                                       const int32_t *hot_cols, const int32_t *hot_cnt, int mem);
+
 /* Everything a conv layer does around the aggregation, fused into the row store of the SpMM
  * (models/pyg_gcn_conv.py:130-137, pyg_gin_conv.py:80-101, models/quantize.py:40-42), plus the multi-GPU exchange.
  * All fields optional (zero = off):

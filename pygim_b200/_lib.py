@@ -23,7 +23,7 @@ SYMBOLS = [
     "pygim_device_info", "pygim_spmm_to_device_group", "pygim_spmm_free_group", "pygim_plan_set_option",
     "pygim_plan_stats", "pygim_spmm_run_group_host", "pygim_spmm_run_group_device", "pygim_spmm_device", "pygim_spmm_device_peers",
     "pygim_last_timers", "pygim_last_launches", "pygim_partition_rows_by_nnz", "pygim_partition_rows_even",
-    "pygim_plan_layout", "pygim_plan_set_row_map", "pygim_spmm_device_ex", "pygim_wait_flags", "pygim_quantize",
+    "pygim_plan_layout", "pygim_plan_set_row_map", "pygim_spmm_device_ex", "pygim_wait_flags", "pygim_quantize", "pygim_plan_set_hot_tiles",
 ]
 
 
@@ -69,6 +69,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pygim_plan_set_row_map.argtypes = [C.c_uint64, vp, i64, ci]
     lib.pygim_spmm_device_ex.argtypes = [C.c_uint64, vp, i64, vp, i64, P(Epilogue), vp]
     lib.pygim_wait_flags.argtypes = [vp, ci, i32, vp]
+    lib.pygim_plan_set_hot_tiles.argtypes = [C.c_uint64, i64, vp, ci, vp, vp, ci]
     lib.pygim_quantize.argtypes = [vp, i64, i64, i64, ci, vp, i64, vp, vp]
     for name in SYMBOLS:
         if name != "pygim_last_error":

@@ -115,6 +115,7 @@ class SparseTensorBase:
         # original row of its row r; the plan scatters on store, so mul() returns rows in the original order
         self.row_perm = None
         self.plan_options = {}
+        self.hot_plan = None       # reorder.hot_cold_plan(...): `raw` is then in hot/cold form (CSR only)
 
     def _plan_created(self):
         """Attach what belongs to the plan besides the sparse arrays: the row map and the tuned options."""
@@ -122,6 +123,11 @@ class SparseTensorBase:
             pim_ops.plan_set_row_map(self.sp_info_ptr, self.row_perm)
         for key, value in self.plan_options.items():
             pim_ops.plan_set_option(self.sp_info_ptr, key, value)
+        if self.hot_plan is not None:
+            assert self.format == "CSR" and len(self.parts) == 1, "hot/cold plans are CSR, sp_parts == 1"
+            pim_ops.plan_set_option(self.sp_info_ptr, "seg_len", self.hot_plan["seg_len"])
+            pim_ops.plan_set_hot_tiles(self.sp_info_ptr, self.hot_plan["super_rows"], self.hot_plan["hot_cols"],
+                                       self.hot_plan["hot_cnt"])
 
     # -- column split of the adjacency (sparse parts; partial products are summed)
     def col_split(self, nparts=4):

@@ -194,6 +194,19 @@ def plan_set_row_map(handle: int, row_map: Optional[torch.Tensor]) -> None:
                                                  _lib.MEM_DEVICE if rm.is_cuda else _lib.MEM_HOST))
 
 
+def plan_set_hot_tiles(handle: int, super_rows: torch.Tensor, hot_cols: torch.Tensor, hot_cnt: torch.Tensor) -> None:
+    """pygim_plan_set_hot_tiles: supertickets at `super_rows` (int32 [S+1]), their tile columns `hot_cols`
+    (int32 [S x K], -1 = unused) and the per-row hot counts (int32 [nrows]); all on one device."""
+    sr, hc, hn = (t.to(torch.int32).contiguous() for t in (super_rows, hot_cols, hot_cnt))
+    if not (sr.is_cuda == hc.is_cuda == hn.is_cuda):
+        raise _lib.PygimError("hot-tile arrays must live on one device")
+    if sr.is_cuda:
+        torch.cuda.current_stream(sr.device).synchronize()
+    _lib.check(_lib.lib().pygim_plan_set_hot_tiles(int(handle), sr.numel() - 1, C.c_void_p(sr.data_ptr()), int(hc.size(1)),
+                                                   C.c_void_p(hc.data_ptr()), C.c_void_p(hn.data_ptr()),
+                                                   _lib.MEM_DEVICE if sr.is_cuda else _lib.MEM_HOST))
+
+
 def plan_stats(handle: int, part: int = 0) -> dict:
     out = (C.c_int64 * 8)()
     _lib.check(_lib.lib().pygim_plan_stats(int(handle), int(part), out))

@@ -70,15 +70,19 @@ class SparseTensorCOO(SparseTensorBase):
 
 def prepare_pim_spmm(adj_t, args):
     """backend_pim/spmm.py:143-147.  Two optional attributes of `args` (absent in the reference's drivers, so they
-    run unchanged) switch on the prepare-time work SURVEY.md 8f lists: `reorder` ("cluster" | "degree"; also the
-    PYGIM_REORDER environment variable) permutes A's rows for L1 locality, and `tune` (True, or ds_parts == 0) lets
+    run unchanged) switch on the prepare-time work SURVEY.md 8f lists: `reorder` ("cluster" | "tiles" | "degree"; also
+    the PYGIM_REORDER environment variable) permutes A's rows so that rows sharing neighbours are adjacent ("tiles"
+    additionally builds the hot/cold plan whose hot feature rows are gathered from shared memory), and `tune` (True, or ds_parts == 0) lets
     utils.autotuner pick the column tiling and the kernel options from the graph statistics."""
     import os
     method = getattr(args, "reorder", None) or os.environ.get("PYGIM_REORDER") or None
-    perm = None
+    perm, hot = None, None
     if method and method != "none":
-        from ..reorder import reorder_rows
-        adj_t, perm, _ = reorder_rows(adj_t, method)
+        from ..reorder import hot_cold_plan, reorder_rows
+        adj_t, perm, stats = reorder_rows(adj_t, method)
+        row_bytes = args.hidden_size * torch.empty((), dtype=args.data_type).element_size()
+        if method == "tiles" and args.sp_format == "CSR" and args.sp_parts == 1 and row_bytes >= 64 and row_bytes % 16 == 0:
+            adj_t, hot = hot_cold_plan(adj_t, stats.get("group_of_row"))
     ds_parts, options = args.ds_parts, {}
     if getattr(args, "tune", False) or not ds_parts:
         from ..utils import autotuner
@@ -88,6 +92,7 @@ def prepare_pim_spmm(adj_t, args):
         ds_parts, options = choice["ds_parts"], choice["options"]
     A = SparseTensorCOO(adj_t, dtype=args.data_type, format=args.sp_format)
     A.row_perm = perm
+    A.hot_plan = hot
     A.plan_options = options
     A.col_split(args.sp_parts)
     A.to_pim_group(args.hidden_size, ds_parts)

@@ -112,7 +112,7 @@ struct CsrPlan {
     int4 *d_supers = nullptr;
     int *d_long_rows = nullptr;
     int *d_long_seg_ptr = nullptr;
-    int n_items = 0, n_super = 0;
+    int n_items = 0, n_super = 0, n_seg_super = 0;
     int n_seg = 0, n_long = 0;
 };
 
@@ -134,6 +134,11 @@ struct SparsePart {
     std::vector<CsrPlan> chunks;   // lazily built by the host entry point
     int seg_len = 0;
     long long max_row_nnz = 0, empty_rows = 0;
+    // hot/cold plan (pygim_plan_set_hot_tiles): row supertickets at the caller's boundaries, each with hot_k tile
+    // columns; colind then holds tile slots for the first hot_cnt[r] nonzeros of row r
+    std::vector<int> hot_super_rows;
+    int *d_hot_cols = nullptr, *d_hot_cnt = nullptr;
+    int hot_k = 0;
     const int *csr_rowptr() const { return d_rowptr ? d_rowptr : rowidx; }
 };
 
@@ -273,12 +278,20 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
             }
         }
     }
+    out.n_seg_super = (int)supers.size();
     {
         long long acc = 0, first = r0;
+        size_t next_cut = 1;               // hot/cold plans: the caller's superticket boundaries
+        const bool fixed = !p.hot_super_rows.empty() && r0 == 0 && r1 == p.nrows;
         for (long long r = r0; r < r1; ++r) {
             const long long n = (long long)(unsigned)rp[r + 1] - (long long)(unsigned)rp[r];
             acc += n > seg_len ? 0 : std::max<long long>(n, 1);
-            if (acc >= super || r + 1 == r1) {
+            bool cut = acc >= super || r + 1 == r1;
+            if (fixed) {
+                cut = (long long)p.hot_super_rows[next_cut] == r + 1;
+                if (cut) ++next_cut;
+            }
+            if (cut) {
                 const long long rows = r + 1 - first;
                 const long long per = std::max<long long>(1, std::min<long long>(max_rows, (target * rows + acc / 2) / std::max<long long>(acc, 1)));
                 const long long items = (rows + per - 1) / per;
@@ -346,6 +359,8 @@ static void destroy_group(Group *g) {
     for (auto &p : g->parts) {
         free_csr_plan(p);
         if (p.d_rowptr) cudaFree(p.d_rowptr);
+        if (p.d_hot_cols) cudaFree(p.d_hot_cols);
+        if (p.d_hot_cnt) cudaFree(p.d_hot_cnt);
         if (p.owned) {
             cudaFree(const_cast<int *>(p.rowidx));
             cudaFree(const_cast<int *>(p.colind));
@@ -500,7 +515,8 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
     if (g->format == PYGIM_CSR || g->csr_view) {
         CsrPlan &pl = plan ? *plan : p.full;
         const long long ldp = (width * (long long)s + 15) / 16 * 16 / (long long)s;
-        const int max_g = g->opt_max_g > 0 ? (int)g->opt_max_g : 32;
+        int max_g = g->opt_max_g > 0 ? (int)g->opt_max_g : 32;
+        if (p.hot_k > 0) max_g = std::min(max_g, 8);      // hot/cold: 128-byte column chunks (one tile row = one line)
         const bool vec = csr_can_vectorize(s, B, C, float_out ? sizeof(float) : s, width, ldb, ldc, ldp);
         const int chunks = csr_col_chunks(s, width, max_g, vec);
         const size_t n_counters = 4 + (size_t)pl.n_super * chunks + (size_t)pl.n_long * chunks;
@@ -535,6 +551,13 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
                                               : (p.nnz < 96 * std::max<long long>(p.nrows, 1) ? 3 : 0);
         l.max_g = max_g;
         l.cta_threads = g->opt_cta_threads > 0 ? (int)g->opt_cta_threads : 256;
+        if (p.hot_k > 0) {
+            if (plan) return fail(PYGIM_ERR_INVALID, "hot/cold plans have no row-range sub-plans");
+            l.hot_cols = p.d_hot_cols;
+            l.hot_cnt = p.d_hot_cnt;
+            l.hot_k = p.hot_k;
+            l.n_seg_super = pl.n_seg_super;
+        }
         l.ncols = width;
         l.ldb = ldb;
         l.ldc = ldc;
@@ -874,6 +897,8 @@ PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int6
     } else {
         return fail(PYGIM_ERR_INVALID, "unknown option '%s'", key);
     }
+    if (rebuild && !g->parts.empty() && g->parts[0].hot_k > 0)
+        return fail(PYGIM_ERR_INVALID, "option '%s' must be set before pygim_plan_set_hot_tiles", key);
     if (rebuild && (g->format == PYGIM_CSR || g->csr_view)) {
         CUDA_TRY(cudaSetDevice(g->device));
         CUDA_TRY(cudaDeviceSynchronize());
@@ -926,6 +951,38 @@ PYGIM_API int pygim_plan_set_row_map(pygim_handle_t handle, const int32_t *row_m
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g->d_row_map), std::max<size_t>((size_t)n, 1) * sizeof(int)));
     CUDA_TRY(cudaMemcpy(g->d_row_map, row_map, (size_t)n * sizeof(int),
                         mem == PYGIM_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_plan_set_hot_tiles(pygim_handle_t handle, int64_t n_super, const int32_t *super_rows, int hot_k,
+                                       const int32_t *hot_cols, const int32_t *hot_cnt, int mem) {
+    Group *g = as_group(handle);
+    if (!g) return PYGIM_ERR_INVALID;
+    if (g->parts.size() != 1) return fail(PYGIM_ERR_INVALID, "hot/cold plans need sp_parts == 1");
+    if (g->format == PYGIM_COO && !g->csr_view) return fail(PYGIM_ERR_INVALID, "hot/cold plans need a CSR plan or a sorted COO plan");
+    if (!super_rows || !hot_cols || !hot_cnt || n_super <= 0 || hot_k <= 0) return fail(PYGIM_ERR_INVALID, "bad hot-tile arguments");
+    SparsePart &p = g->parts[0];
+    CUDA_TRY(cudaSetDevice(g->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<int> rows((size_t)n_super + 1);
+    const cudaMemcpyKind to_host = mem == PYGIM_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost;
+    const cudaMemcpyKind to_dev = mem == PYGIM_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpy(rows.data(), super_rows, rows.size() * sizeof(int), to_host));
+    if (rows[0] != 0 || rows[(size_t)n_super] != (int)p.nrows) return fail(PYGIM_ERR_INVALID, "superticket rows must span [0, nrows]");
+    for (int64_t k = 0; k < n_super; ++k)
+        if (rows[(size_t)k + 1] <= rows[(size_t)k]) return fail(PYGIM_ERR_INVALID, "superticket %lld is empty", (long long)k);
+    if ((size_t)hot_k * 8 * 16 > (size_t)200 * 1024) return fail(PYGIM_ERR_INVALID, "hot_k %d does not fit shared memory", hot_k);
+    if (p.d_hot_cols) { cudaFree(p.d_hot_cols); p.d_hot_cols = nullptr; }
+    if (p.d_hot_cnt) { cudaFree(p.d_hot_cnt); p.d_hot_cnt = nullptr; }
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&p.d_hot_cols), (size_t)n_super * hot_k * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(p.d_hot_cols, hot_cols, (size_t)n_super * hot_k * sizeof(int), to_dev));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&p.d_hot_cnt), std::max<size_t>((size_t)p.nrows, 1) * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(p.d_hot_cnt, hot_cnt, (size_t)p.nrows * sizeof(int), to_dev));
+    p.hot_super_rows = rows;
+    p.hot_k = 0;                       // replan with the fixed boundaries, then switch the mode on
+    int rc = replan(g);
+    if (rc) return rc;
+    p.hot_k = hot_k;
     return PYGIM_OK;
 }
 
@@ -1075,7 +1132,8 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
 
     // ---- row chunks of the last tile (CSR only: COO chunks are nnz ranges, not row ranges)
     int n_chunks = 1;
-    if (pipelined && (g->format == PYGIM_CSR || g->csr_view) && !g->d_row_map && g->parts[0].nnz >= 4096 && rowsC >= 64) {
+    if (pipelined && (g->format == PYGIM_CSR || g->csr_view) && !g->d_row_map && g->parts[0].hot_k == 0 &&
+        g->parts[0].nnz >= 4096 && rowsC >= 64) {
         n_chunks = g->opt_host_chunks > 0 ? (int)g->opt_host_chunks : 4;
         if (g->parts[0].chunks.size() != (size_t)n_chunks) {
             std::vector<int64_t> split((size_t)n_chunks + 1);

@@ -3,6 +3,7 @@
 #include "launch.h"
 #include "spmm_coo.cuh"
 #include "spmm_csr.cuh"
+#include "spmm_csr_hc.cuh"
 
 #ifndef PYGIM_T
 #error "compile with -DPYGIM_T=<type> -DPYGIM_SFX=<suffix>"
@@ -114,6 +115,36 @@ static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t
     return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>>(a, l, launches);
 }
 
+// hot/cold kernel: one block per SM, dynamic shared memory = the tile
+template <int E, int G, bool UNIT>
+static cudaError_t launch_csr_hc(const CsrArgs<T> &a0, const CsrLaunch &l, int64_t *launches) {
+    constexpr int THREADS = 512;
+    constexpr int NV = (E >= 8) ? 1 : (UNIT ? 4 : 2);
+    auto kernel = csr_hc_kernel<T, E, G, NV, THREADS, UNIT>;
+    const size_t smem = (size_t)l.hot_k * G * 16;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
+    HcArgs<T> h;
+    h.c = a0;
+    h.c.col_chunks = (a0.nvec + G - 1) / G;
+    h.hot_cols = l.hot_cols;
+    h.hot_cnt = l.hot_cnt;
+    h.hot_k = l.hot_k;
+    h.n_seg_super = l.n_seg_super;
+    int threads = l.cta_threads > 256 ? l.cta_threads : THREADS;
+    threads = (threads + 31) / 32 * 32;
+    if (threads > THREADS) threads = THREADS;
+    const int blocks = l.sm_count > 0 ? l.sm_count : 148;
+    h.c.n_warps = (unsigned)(blocks * (threads / 32));
+    kernel<<<blocks, threads, smem, l.stream>>>(h);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *launches) {
     CsrArgs<T> a;
     a.rowptr = l.rowptr;
@@ -163,6 +194,15 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
     }
     if (l.n_items == 0 || a.nvec == 0) return cudaSuccess;
     cudaError_t err;
+    if (l.hot_k > 0) {
+        if constexpr (sizeof(T) * E == 16) {
+            const int g = csr_lanes(a.nvec, l.max_g < 8 ? l.max_g : 8);
+            const bool u = l.unit_values != 0;
+            if (g >= 8) return u ? launch_csr_hc<E, 8, true>(a, l, launches) : launch_csr_hc<E, 8, false>(a, l, launches);
+            if (g == 4) return u ? launch_csr_hc<E, 4, true>(a, l, launches) : launch_csr_hc<E, 4, false>(a, l, launches);
+        }
+        return cudaErrorInvalidValue;     // hot/cold plans need 16-byte words and dense rows of at least 64 bytes
+    }
 #define PYGIM_CSR_CASE(GV) \
     case GV: err = l.unit_values ? launch_csr_g<E, GV, true>(a, l, launches) : launch_csr_g<E, GV, false>(a, l, launches); break
     switch (csr_lanes(a.nvec, l.max_g)) {

@@ -47,6 +47,11 @@ struct CsrLaunch {
     long long ldb, ldc, ldp;  // row strides in elements (ldc in elements of the OUTPUT type)
     int accumulate;
     int unit_values;          // every stored value is one: skip the value stream (bit-identical result)
+    // hot/cold plans (spmm_csr_hc.cuh): hot_k > 0 => colind holds tile slots for the first hot_cnt[r] nonzeros of row r
+    const int *hot_cols = nullptr;   // [row supertickets x hot_k]
+    const int *hot_cnt = nullptr;    // [nrows]
+    int hot_k = 0;
+    int n_seg_super = 0;
     EpilogueLaunch epi;
     int sm_count;
     cudaStream_t stream;

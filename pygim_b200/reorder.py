@@ -107,15 +107,113 @@ def cluster_rows(adj: SparseTensor, n_pivots: Optional[int] = None, seed: int = 
     perm = torch.argsort(arg, stable=True)
     groups = int(torch.unique(arg).numel())
     stats = {"pivots": P, "groups": groups, "assigned": float((arg < P).float().mean()),
-             "mean_shared": float(best.clamp(min=0).mean()), "mean_degree": float(deg.float().mean())}
+             "mean_shared": float(best.clamp(min=0).mean()), "mean_degree": float(deg.float().mean()),
+             "group_of_row": arg[perm]}           # group of every row of the NEW order
     return perm, stats
+
+
+def auto_seg_len(nnz: int, sm_count: int = 148, threads_per_sm: int = 2048) -> int:
+    """The plan's automatic segment length (csrc/backend_pim.cu::auto_seg_len), needed here because rows that will be
+    cut into segments must stay all-cold."""
+    s = nnz // max(1, sm_count * (threads_per_sm // 32) * 8)
+    p = 512
+    while p < s and p < 4096:
+        p *= 2
+    return p
+
+
+def hot_cold_plan(adj: SparseTensor, group_of_row: Optional[torch.Tensor] = None, hot_k: int = 1280,
+                  seg_len: Optional[int] = None, super_nnz: int = 65536) -> Tuple[SparseTensor, dict]:
+    """Hot/cold form of a (row-clustered) adjacency for csrc/spmm_csr_hc.cuh.
+
+    The rows are cut into supertickets of about `super_nnz` nonzeros (never across the groups in `group_of_row`,
+    small neighbouring groups are merged); per superticket the `hot_k` most referenced columns become its shared-memory
+    tile.  Returns the re-encoded adjacency - every row's hot nonzeros first, holding TILE SLOTS instead of column
+    ids, values moved along - and {"super_rows", "hot_cols", "hot_cnt", "seg_len", "coverage"} for
+    pygim_plan_set_hot_tiles.  Rows longer than `seg_len` (cut into segments by the plan) stay all-cold."""
+    rowptr, col, value = adj.csr()
+    dev = col.device
+    n, m = adj.size(0), adj.size(1)
+    nnz = int(col.numel())
+    seg_len = int(seg_len or auto_seg_len(nnz))
+    deg = rowptr[1:] - rowptr[:-1]
+    short = deg <= seg_len
+    w = torch.where(short, deg, torch.zeros_like(deg))
+    cum = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(w, 0, out=cum[1:])
+    cum_h = cum.cpu()
+    # ---- superticket boundaries (host loop over the groups: a few thousand iterations)
+    if group_of_row is not None and n > 0:
+        g = group_of_row.to(dev)
+        change = torch.nonzero(g[1:] != g[:-1]).flatten() + 1
+        bounds = [0] + change.cpu().tolist() + [n]
+    else:
+        bounds = [0, n]
+    cuts = [0]
+    pending = 0                      # start row of groups merged so far
+    for gi in range(len(bounds) - 1):
+        ge = bounds[gi + 1]
+        load = int(cum_h[ge] - cum_h[pending])
+        if load < super_nnz // 2 and ge < n:
+            continue                  # too little work for a tile of its own: merge with the next group
+        pieces = max(1, int(round(load / super_nnz)))
+        base = int(cum_h[pending])
+        targets = torch.tensor([base + (load * j) // pieces for j in range(1, pieces)], dtype=torch.int64)
+        inner = torch.searchsorted(cum_h, targets).tolist() if pieces > 1 else []
+        for r in inner:
+            r = min(max(int(r), cuts[-1] + 1), ge - 1)
+            if r > cuts[-1]:
+                cuts.append(r)
+        if ge > cuts[-1]:
+            cuts.append(ge)
+        pending = ge
+    if cuts[-1] != n:
+        cuts.append(n)
+    super_rows = torch.tensor(cuts, dtype=torch.int64, device=dev)
+    S = super_rows.numel() - 1
+    st_of_row = torch.repeat_interleave(torch.arange(S, device=dev), super_rows[1:] - super_rows[:-1])
+    # ---- hot columns: the hot_k most referenced columns of each superticket (short rows only)
+    e_row = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+    e_short = short[e_row]
+    key = st_of_row[e_row] * m + col
+    uniq, counts = torch.unique(key[e_short], return_counts=True)       # sorted
+    ust = uniq // m
+    o1 = torch.argsort(counts, descending=True, stable=True)
+    order = o1[torch.argsort(ust[o1], stable=True)]                     # by superticket, most referenced first
+    ust_o = ust[order]
+    seg_start = torch.searchsorted(ust_o, torch.arange(S, device=dev))
+    rank = torch.arange(order.numel(), device=dev) - seg_start[ust_o]
+    hot = (rank < hot_k) & (counts[order] >= 2)                          # a column used once gains nothing
+    hot_cols = torch.full((S, hot_k), -1, dtype=torch.int32, device=dev)
+    hot_cols[ust_o[hot], rank[hot]] = (uniq[order][hot] % m).to(torch.int32)
+    hk, hk_perm = torch.sort(uniq[order][hot])
+    hslot = rank[hot][hk_perm]
+    del uniq, counts, ust, o1, order, ust_o, rank
+    if hk.numel():
+        pos = torch.searchsorted(hk, key).clamp_(max=hk.numel() - 1)
+        is_hot = e_short & (hk[pos] == key)
+        slot = hslot[pos]
+    else:
+        is_hot = torch.zeros_like(e_short)
+        slot = torch.zeros_like(col)
+    del key, e_short
+    # ---- every row hot-first
+    order2 = torch.argsort(e_row * 2 + (~is_hot).to(torch.int64), stable=True)
+    new_col = torch.where(is_hot, slot, col)[order2]
+    new_val = None if value is None else value[order2]
+    hot_cnt = torch.bincount(e_row[is_hot], minlength=n).to(torch.int32)
+    coverage = float(is_hot.float().mean()) if nnz else 0.0
+    out = SparseTensor(rowptr=rowptr, col=new_col, value=new_val, sparse_sizes=(n, m), is_sorted=True)
+    return out, {"super_rows": super_rows.to(torch.int32), "hot_cols": hot_cols, "hot_cnt": hot_cnt, "seg_len": seg_len,
+                 "coverage": coverage, "supertickets": S, "hot_k": hot_k}
 
 
 def reorder_rows(adj: SparseTensor, method: str = "cluster", **kw) -> Tuple[SparseTensor, torch.Tensor, dict]:
     """(row-permuted adjacency, perm, stats).  perm[r] = original row of new row r - exactly the row map the plan
-    needs.  Methods: "cluster" (shared-neighbour pivots), "degree" (rows by descending degree - keeps rows of
+    needs.  Methods: "cluster" (shared-neighbour pivots), "tiles" (the same order; the caller then builds the
+    hot/cold plan with hot_cold_plan(adj, stats["group_of_row"])), "degree" (rows by descending degree - keeps rows of
     similar length together, which evens out the work items; no locality claim)."""
-    if method == "cluster":
+    if method in ("cluster", "tiles"):
         perm, stats = cluster_rows(adj, **kw)
     elif method == "degree":
         rowptr = adj.csr()[0]

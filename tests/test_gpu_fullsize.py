@@ -73,5 +73,7 @@ def test_clustered_reddit_shape_with_prepare_time_reordering(gpu_backend, oracle
     results in the original row order, every element equal."""
     g = _graph("reddit", clustered=True)
     _check(oracle, *g, torch.float32, "CSR", 32, reorder="cluster")
+    _check(oracle, *g, torch.float32, "CSR", 32, reorder="tiles")
+    _check(oracle, *g, torch.float32, "CSR", 128, reorder="tiles")
     del g
     torch.cuda.empty_cache()

@@ -119,6 +119,47 @@ def test_row_map_and_prepare_time_clustering(gpu_backend, oracle, fmt):
     assert same > 0.85 and stats["assigned"] > 0.9, (same, stats)
 
 
+@pytest.mark.parametrize("weighted", [False, True])
+def test_hot_cold_tiles(gpu_backend, oracle, weighted):
+    """reorder="tiles": rows clustered, hot feature rows staged in shared memory (csrc/spmm_csr_hc.cuh).  Same results
+    as the oracle in the ORIGINAL row order - across column chunks (H x s > 128 bytes), segments of long rows (all
+    cold), weighted values moved along with their nonzeros, host and device operands."""
+    from pygim_b200 import graphgen, reorder
+    from pygim_b200.backend_pim.spmm import SparseTensorCOO, prepare_pim_spmm
+    from pygim_b200.sparse_tensor import SparseTensor
+    n, nnz = 6000, 600_000
+    rowptr, col = graphgen.clustered_csr(n, nnz, 2500, seed=4, community=300, p_in=0.7)
+    for dtype, hidden in ((torch.float32, 32), (torch.float32, 128), (torch.float32, 16), (torch.int32, 48), (torch.int8, 64),
+                          (torch.float64, 8), (torch.int16, 40)):
+        val = None
+        if weighted:
+            val = torch.from_numpy(np.random.default_rng(1).integers(-3, 4, nnz)).to(dtype)
+        adj = SparseTensor(rowptr=rowptr, col=col, value=val, sparse_sizes=(n, n), is_sorted=True)
+        x = features(n, hidden, dtype, seed=5)
+        want = _want(oracle, adj, x)
+        args = make_args(dtype, "CSR", hidden)
+        args.reorder = "tiles"
+        A = prepare_pim_spmm(adj.to("cuda"), args)
+        assert A.hot_plan is not None and A.hot_plan["coverage"] > 0.3, (dtype, hidden)
+        for _ in range(2):
+            got = A.mul(x.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(got.cpu(), want), (dtype, hidden, weighted)
+        assert torch.equal(A.mul(x), want), (dtype, hidden, weighted, "host operand")
+        A.free()
+    # explicit small tile, tiny supertickets, long rows cut into segments
+    adj = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(n, n), is_sorted=True).to("cuda")
+    radj, perm, stats = reorder.reorder_rows(adj, "tiles", n_pivots=64)
+    hc, hot = reorder.hot_cold_plan(radj, stats["group_of_row"], hot_k=96, seg_len=128, super_nnz=4096)
+    x = features(n, 64, torch.float32, seed=6)
+    A = SparseTensorCOO(hc, dtype=torch.float32, format="CSR")
+    A.row_perm, A.hot_plan = perm, hot
+    A.to_pim_group(64, 1)
+    assert gpu_backend.plan_stats(A.sp_info_ptr)["segments"] > 0
+    assert torch.equal(A.mul(x.cuda()).cpu(), _want(oracle, adj.to("cpu"), x))
+    A.free()
+
+
 def test_sorted_coo_runs_through_the_csr_kernels_and_unsorted_coo_is_still_right(gpu_backend, oracle):
     from pygim_b200.backend_pim.spmm import prepare_pim_spmm
     adj = _reddit_like(0.006, seed=7)
