@@ -877,7 +877,7 @@ def main():
                     help="N > 1: all-gather fused into the kernel epilogue (peer stores) or a separate NCCL collective")
     ap.add_argument("--no-multicast", action="store_true", help="fused gather: per-peer stores instead of multimem.st")
     ap.add_argument("--chunks", type=int, default=1, help="N > 1: sub-blocks per rank (all-gather/compute overlap)")
-    ap.add_argument("--short-rows", type=int, default=None, choices=[0, 1, 2, 3],
+    ap.add_argument("--short-rows", type=int, default=None, choices=[0, 1, 2, 3, 4],
                     help="force the CSR instantiation: 0 deep unroll, 1 high occupancy, 2 streamed row tickets")
     ap.add_argument("--no-l2-persist", action="store_true",
                     help="do not put the access-policy window (persisting L2) over the dense tile")

@@ -117,8 +117,8 @@ PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle);
  *   max_g            lanes per dense row are capped at this power of two; wider rows run as column chunks of one
  *                    launch (8 = 128-byte chunks, the L1 line)
  *   short_rows       CSR kernel family: 0 deep (128 registers, 16 gathers per lane in flight), 1 high occupancy
- *                    (40 registers), 2 streamed row items, 3 light (64 registers, 8 gathers); automatic: 3 when the
- *                    mean degree is below 96, else 0
+ *                    (40 registers), 2 streamed row items, 3 light (64 registers, 8 gathers), 4 one lane group per
+ *                    row; automatic: 4 when the mean degree is below 12, 3 below 96, else 0
  *   unit_values      0 forces the general kernels even when every stored value is one
  *   coo_native       1 runs a sorted COO plan through the COO (segmented reduction) kernel instead of the CSR
  *                    kernels over the derived row pointer

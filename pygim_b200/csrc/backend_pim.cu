@@ -546,9 +546,11 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.seg_len = p.seg_len;
         l.nnz_total = p.nnz;
         // kernel family: 0 deep (128 registers, 16 gathers in flight) for long rows; 3 light (64 registers, twice the
-        // warps) for short rows; 1 high occupancy and 2 streamed row items stay selectable
+        // warps) for short rows; 4 one lane group per row for very short rows (citation graphs); 1 high occupancy
+        // and 2 streamed row items stay selectable
+        const long long rows1 = std::max<long long>(p.nrows, 1);
         l.short_rows = g->opt_short_rows >= 0 ? (int)g->opt_short_rows
-                                              : (p.nnz < 96 * std::max<long long>(p.nrows, 1) ? 3 : 0);
+                                              : (p.nnz < 12 * rows1 ? 4 : (p.nnz < 96 * rows1 ? 3 : 0));
         l.max_g = max_g;
         l.cta_threads = g->opt_cta_threads > 0 ? (int)g->opt_cta_threads : 256;
         if (p.hot_k > 0) {

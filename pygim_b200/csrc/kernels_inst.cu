@@ -73,7 +73,7 @@ template <int E, int G> struct CooTune {
     static constexpr int MIN_BLOCKS = (E >= 8) ? 2 : 3;
 };
 
-template <int E, int G, bool UNIT, typename Tune, bool STREAM = false>
+template <int E, int G, bool UNIT, typename Tune, int STREAM = 0>
 static cudaError_t launch_csr_t(CsrArgs<T> a, const CsrLaunch &l, int64_t *launches) {
     auto kernel = csr_spmm_kernel<T, E, G, Tune::NV, Tune::THREADS, Tune::MIN_BLOCKS, UNIT, STREAM>;
     int threads = l.cta_threads > 0 ? l.cta_threads : 256;
@@ -108,18 +108,22 @@ static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t
     // the 16-byte-word instantiations of 32/64-bit types come in two register budgets (see CsrTuneShort)
     // (rows of 512 bytes and more - G == 32 - gain nothing from either: measured 5.11 vs 4.97 ms on products-shape)
     if constexpr (E < 8 && sizeof(T) * E >= 16 && G < 32) {
-        if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTuneStream<E, UNIT>, true>(a, l, launches);   // streamed
+        if (l.short_rows == 2) return launch_csr_t<E, G, UNIT, CsrTuneStream<E, UNIT>, 1>(a, l, launches);   // streamed
         if (l.short_rows == 1) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, UNIT>>(a, l, launches);
     }
     if (l.short_rows == 3) return launch_csr_t<E, G, UNIT, CsrTuneLight<E, UNIT>>(a, l, launches);
+    if (l.short_rows == 4) return launch_csr_t<E, G, UNIT, CsrTuneLight<E, UNIT>, 2>(a, l, launches);   // lane group per row
     return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>>(a, l, launches);
 }
 
 // hot/cold kernel: one block per SM, dynamic shared memory = the tile
 template <int E, int G, bool UNIT>
 static cudaError_t launch_csr_hc(const CsrArgs<T> &a0, const CsrLaunch &l, int64_t *launches) {
-    constexpr int THREADS = 512;
-    constexpr int NV = (E >= 8) ? 1 : (UNIT ? 4 : 2);
+#ifndef PYGIM_HC_THREADS
+#define PYGIM_HC_THREADS 512
+#endif
+    constexpr int THREADS = PYGIM_HC_THREADS;
+    constexpr int NV = (E >= 8) ? 1 : (THREADS > 768 ? 1 : (THREADS > 512 ? 2 : (UNIT ? 4 : 2)));
     auto kernel = csr_hc_kernel<T, E, G, NV, THREADS, UNIT>;
     const size_t smem = (size_t)l.hot_k * G * 16;
     static size_t smem_set = 0;
@@ -135,9 +139,7 @@ static cudaError_t launch_csr_hc(const CsrArgs<T> &a0, const CsrLaunch &l, int64
     h.hot_cnt = l.hot_cnt;
     h.hot_k = l.hot_k;
     h.n_seg_super = l.n_seg_super;
-    int threads = l.cta_threads > 256 ? l.cta_threads : THREADS;
-    threads = (threads + 31) / 32 * 32;
-    if (threads > THREADS) threads = THREADS;
+    int threads = THREADS;
     const int blocks = l.sm_count > 0 ? l.sm_count : 148;
     h.c.n_warps = (unsigned)(blocks * (threads / 32));
     kernel<<<blocks, threads, smem, l.stream>>>(h);

@@ -82,6 +82,7 @@ template <typename T> struct CsrArgs {
     int *super_cnt;             // [n_super x col_chunks] items drawn per (superticket, column chunk); zero at rest
     int *seg_count;             // [col_chunks x n_long] arrival counters, zero at rest
     unsigned int *warps_out;    // warps that have left the kernel; zero at rest (the last one resets everything)
+                                // warps_out[1]: (superticket, chunk) units whose items have ALL been drawn
     unsigned int n_warps;       // warps of this launch
     int n_super, n_seg, n_long;
     int nrows;
@@ -579,6 +580,63 @@ __device__ __forceinline__ void csr_stream_rows(const CsrArgs<T> &a, int first, 
     }
 }
 
+// SHORT ROWS, lean path: one LANE GROUP per row.  The P = 32/G lane groups of a warp take P consecutive rows of the
+// item at a time; a group walks its own row nonzero by nonzero (index load broadcast inside the group, one 16-byte
+// gather per lane, UQ nonzeros in flight), so a row's sum never leaves its group: no shuffle tree, no alignment
+// prologue, no per-row loop setup - about 2 warp instructions per nonzero instead of ~230 per ROW on the
+// warp-wide path (arxiv-shape, mean degree 7: 34 -> 3 instructions per nonzero).  Rows longer than `wide_from`
+// would leave the other groups idle; they are returned as a bit mask and processed warp-wide by the caller.
+template <typename T, int E, int G, int UQ, bool UNIT>
+__device__ __forceinline__ unsigned csr_rows_by_group(const CsrArgs<T> &a, int first, int count, int rp, int chunk,
+                                                      int wide_from) {
+    using Acc = typename Arith<T>::Acc;
+    using Shfl = typename Arith<T>::Shfl;
+    constexpr int P = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int vec = chunk * G + (lane % G);
+    const bool active = vec < a.nvec;
+    const T *Bcol = a.B + (long long)vec * E;
+    asm volatile("" : "+l"(Bcol));
+    const int deg = __shfl_down_sync(FULL, rp, 1) - rp;
+    const unsigned wide = __ballot_sync(FULL, lane < count && deg > wide_from);
+    for (int j0 = 0; j0 < count; j0 += P) {
+        const int j = j0 + sub;
+        const int jj = min(j, count - 1);
+        int i = __shfl_sync(FULL, rp, jj);
+        int end = __shfl_sync(FULL, rp, jj + 1);
+        const bool mine = j < count && !((wide >> jj) & 1u) && active;
+        if (!mine) end = i;
+        Acc acc[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+        while (i < end) {
+            int c[UQ];
+            Shfl v[UQ];
+#pragma unroll
+            for (int u = 0; u < UQ; ++u) {
+                c[u] = 0;
+                v[u] = (Shfl)1;
+                if (i + u < end) {
+                    c[u] = ld_stream(a.colind + i + u);
+                    if constexpr (!UNIT) v[u] = ld_stream(a.val + i + u);
+                }
+            }
+            Pack<T, E> b[UQ];
+#pragma unroll
+            for (int u = 0; u < UQ; ++u)
+                if (i + u < end) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, c[u], a.ldb_bytes));
+#pragma unroll
+            for (int u = 0; u < UQ; ++u)
+                if (i + u < end) fma_pack<T, E>(acc, b[u], v[u]);
+            i += UQ;
+        }
+        if (mine) csr_emit<T, E>(a, acc, first + j, vec);
+    }
+    return wide;
+}
+
 // ---------------------------------------------------------------------------------------------- scheduling
 struct CsrItem {
     int long_idx;      // segment: its long row; rows: -1
@@ -624,7 +682,7 @@ template <typename T> __device__ __forceinline__ void csr_leave(const CsrArgs<T>
     if (left != a.n_warps - 1u) return;
     const int n = a.n_super * a.col_chunks;
     for (int i = lane; i < n; i += 32) a.super_cnt[i] = 0;
-    if (lane == 0) *a.warps_out = 0u;
+    if (lane == 0) { a.warps_out[0] = 0u; a.warps_out[1] = 0u; }
     if (a.epi.n_peers > 0 && a.epi.flags[0] != nullptr) {
         __threadfence_system();           // every warp's rows (observed through the counter) before the flags
         if (lane < a.epi.n_peers)
@@ -635,14 +693,25 @@ template <typename T> __device__ __forceinline__ void csr_leave(const CsrArgs<T>
 
 // Persistent, SM-affine grid.  (superticket s, column chunk c) has index s * col_chunks + c.
 // THREADS only bounds the register allocation: the launcher picks the block size (256 .. THREADS).
-template <typename T, int E, int G, int NV, int THREADS, int MIN_BLOCKS, bool UNIT, bool STREAM = false>
+template <typename T, int E, int G, int NV, int THREADS, int MIN_BLOCKS, bool UNIT, int STREAM = 0>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __grid_constant__ CsrArgs<T> a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n_units = a.n_super * a.col_chunks;
 
     auto process = [&](const CsrItem &cur, int chunk) {
-        if (STREAM && cur.long_idx < 0) {
+        if (STREAM == 2 && cur.long_idx < 0) {
+            // one lane group per row; rows too long for that (but not segmented) warp-wide afterwards
+            unsigned wide = csr_rows_by_group<T, E, G, 4, UNIT>(a, cur.first, cur.count, cur.rp, chunk, 8 * (32 / G) + 32);
+            while (wide) {
+                const int j = __ffs(wide) - 1;
+                wide &= wide - 1;
+                const int start = __shfl_sync(FULL, cur.rp, j);
+                const int end = __shfl_sync(FULL, cur.rp, j + 1);
+                if (end - start <= a.seg_len)
+                    csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.first + j, -1);
+            }
+        } else if (STREAM == 1 && cur.long_idx < 0) {
             // rows longer than seg_len are covered by their segments: stream the row blocks between them
             const int deg = __shfl_down_sync(FULL, cur.rp, 1) - cur.rp;
             const unsigned long_rows = __ballot_sync(FULL, lane < cur.count && deg > a.seg_len);
@@ -677,11 +746,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
         int pend = 0;                                   // lane 0: a ticket whose atomic may still be in flight
         if (lane == 0) pend = atomicAdd(cnt, 1);
         int it = __shfl_sync(FULL, pend, 0);
-        if (lane == 0) pend = atomicAdd(cnt, 1);
+        if (lane == 0) {
+            if (it == n) atomicAdd(a.warps_out + 1, 1u);          // exactly one warp draws ticket n: the unit is drawn out
+            pend = atomicAdd(cnt, 1);
+        }
         CsrItem cur;
         if (it < n) cur = csr_load_item<T>(a, sp, it);
         while (it < n) {
             const int nit = __shfl_sync(FULL, pend, 0);          // drawn one item ago
+            if (lane == 0 && nit == n) atomicAdd(a.warps_out + 1, 1u);
             CsrItem nxt;
             if (nit < n) {
                 if (lane == 0) pend = atomicAdd(cnt, 1);         // for the item after next: not awaited here
@@ -708,6 +781,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             home += (int)nsmid;
         } else {
             while (scan_m == 0 && scan_o < n_units) {
+                if (*(volatile unsigned int *)(a.warps_out + 1) >= (unsigned)n_units) {     // nothing left to draw anywhere
+                    scan_o = n_units;
+                    break;
+                }
                 const int base = (int)(((unsigned long long)smid * 2654435761ull) % (unsigned)n_units);
                 scan_u = base + scan_o + lane;
                 if (scan_u >= n_units) scan_u -= n_units;

@@ -203,7 +203,8 @@ def kernel_options(stats: GraphStats, hidden: int, elem_size: int, reordered: bo
     short = stats.mean_degree < 96
     # kernel family: deep (128 registers, 16 gathers in flight) for long rows, light (64 registers, twice the warps)
     # for short rows; measured: Reddit-shape 9290 vs 8500 GFLOP/s, products-shape 2314 vs 2656
-    opts["short_rows"] = 3 if short else 0
+    # very short rows (citation graphs, mean degree < 12): one lane group per row (arxiv-shape 0.115 vs 0.146 ms)
+    opts["short_rows"] = (4 if stats.mean_degree < 12 else 3) if short else 0
     # work items: ~256 nonzeros; very short rows are capped by the 31-row limit, so aim lower to keep items even
     opts["item_nnz"] = 256 if stats.mean_degree >= 8 else 128
     if reordered:
@@ -218,7 +219,7 @@ def candidate_options(stats: GraphStats, hidden: int, elem_size: int, reordered:
     """The (small) space a measured search walks: the analytic pick first, then its neighbours."""
     base = kernel_options(stats, hidden, elem_size, reordered)
     out = [dict(base)]
-    for sr in (0, 2, 3):
+    for sr in (0, 2, 3, 4):
         if sr != base["short_rows"]:
             out.append({**base, "short_rows": sr})
     for item in (128, 512):
