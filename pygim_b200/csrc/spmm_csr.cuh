@@ -781,7 +781,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             home += (int)nsmid;
         } else {
             while (scan_m == 0 && scan_o < n_units) {
-                if (*(volatile unsigned int *)(a.warps_out + 1) >= (unsigned)n_units) {     // nothing left to draw anywhere
+                // nothing left to draw anywhere?  ONE lane reads the counter: lanes that are not converged here (e.g.
+                // inactive column lanes run ahead) must not see different values and part ways around the ballot
+                unsigned drawn = 0;
+                if (lane == 0) drawn = *(volatile unsigned int *)(a.warps_out + 1);
+                if (__shfl_sync(FULL, drawn, 0) >= (unsigned)n_units) {
                     scan_o = n_units;
                     break;
                 }
