@@ -231,7 +231,13 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
     std::vector<int> long_rows, long_ptr;
     long_ptr.push_back(0);
     const std::vector<int> &rp = p.h_rowptr;
-    const long long target = g.opt_item_nnz > 0 ? g.opt_item_nnz : 256;
+    // ~256 nonzeros per item, fewer on small graphs so that every resident warp still gets about four items
+    long long target = g.opt_item_nnz;
+    if (target <= 0) {
+        const long long want = p.nnz / std::max<long long>(1, 4LL * g_ctx.sm_count * 32);
+        target = 64;
+        while (target * 2 <= want && target < 256) target *= 2;
+    }
     const int max_rows = (int)std::max<long long>(1, std::min<long long>(31, g.opt_rows_per_ticket > 0 ? g.opt_rows_per_ticket : 31));
     long long short_nnz = 0;
     for (long long r = r0; r < r1; ++r) {

@@ -205,8 +205,12 @@ def kernel_options(stats: GraphStats, hidden: int, elem_size: int, reordered: bo
     # for short rows; measured: Reddit-shape 9290 vs 8500 GFLOP/s, products-shape 2314 vs 2656
     # very short rows (citation graphs, mean degree < 12): one lane group per row (arxiv-shape 0.115 vs 0.146 ms)
     opts["short_rows"] = (4 if stats.mean_degree < 12 else 3) if short else 0
-    # work items: ~256 nonzeros; very short rows are capped by the 31-row limit, so aim lower to keep items even
-    opts["item_nnz"] = 256 if stats.mean_degree >= 8 else 128
+    # work items: ~256 nonzeros, fewer on small graphs so that every resident warp still gets about four items
+    # (the library's own default, csrc/backend_pim.cu::build_plan_range)
+    want, item = stats.nnz // (4 * 148 * 32), 64
+    while item * 2 <= want and item < 256:
+        item *= 2
+    opts["item_nnz"] = item
     if reordered:
         # rows that share neighbours are adjacent: let an SM's warps share one superticket's working set, and keep
         # a gathered chunk to one 128-byte L1 line per dense row so the community's rows fit the L1
@@ -222,7 +226,7 @@ def candidate_options(stats: GraphStats, hidden: int, elem_size: int, reordered:
     for sr in (0, 2, 3, 4):
         if sr != base["short_rows"]:
             out.append({**base, "short_rows": sr})
-    for item in (128, 512):
+    for item in (64, 128, 256, 512):
         if item != base["item_nnz"]:
             out.append({**base, "item_nnz": item})
     if hidden * elem_size > 128:
