@@ -808,20 +808,32 @@ def run_inference(a):
     feats, classes = 602, 41                                      # Reddit's feature / class counts
     torch.manual_seed(0)
     x = torch.randn(n, feats, device="cuda")
+    from pygim_b200.models import layers
     results = {}
     for name, net in (("gcn", GCN), ("gin", GIN), ("sage", SAGE)):
         model = net(feats, hidden, classes, 2).cuda().eval()
-        with torch.no_grad():
-            for _ in range(max(a.warmup, 3)):
-                model(x, A)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(a.steps):
-                y = model(x, A)
-            e1.record()
-            torch.cuda.synchronize()
-        results[name] = {"gpu_infer_ms": e0.elapsed_time(e1) / a.steps, "finite": bool(torch.isfinite(y).all())}
+        rec = {}
+        outs = {}
+        for key, fused in (("gpu_infer_ms", True), ("gpu_infer_ms_unfused_epilogue", False)):
+            # fused: quantise = 2 kernels, de-quantise (+ GIN's (1+eps) x) inside the SpMM's row store;
+            # unfused: the reference's torch expressions around A.mul (models/quantize.py:20-42)
+            layers.FUSED_EPILOGUE = fused
+            with torch.no_grad():
+                for _ in range(max(a.warmup, 3)):
+                    model(x, A)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(a.steps):
+                    y = model(x, A)
+                e1.record()
+                torch.cuda.synchronize()
+            rec[key] = e0.elapsed_time(e1) / a.steps
+            outs[key] = y
+        layers.FUSED_EPILOGUE = True
+        rec["finite"] = bool(torch.isfinite(y).all())
+        rec["fused_equals_unfused"] = bool(torch.equal(outs["gpu_infer_ms"], outs["gpu_infer_ms_unfused_epilogue"]))
+        results[name] = rec
     cpu = None
     if not a.no_cpu:
         from oracle import oracle as O

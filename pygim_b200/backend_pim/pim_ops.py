@@ -451,6 +451,10 @@ def spmm_run_dense_many(handles: Sequence[int], Bs: Sequence[torch.Tensor], outs
     per-call host entry point (spmm_run_dense with a host operand) exposes the first upload and the last download of
     EVERY call; this exposes them once per batch."""
     assert len(handles) == len(Bs) == len(outs)
+    # largest operand first: its upload, kernel and download are the longest chain, so it must not be the last to
+    # start (the results are independent, the order is free)
+    order = sorted(range(len(handles)), key=lambda k: -Bs[k].numel())
+    handles, Bs, outs = [handles[k] for k in order], [Bs[k] for k in order], [outs[k] for k in order]
     metas = [_meta(h) for h in handles]
     dev = metas[0].device
     st = _MANY_STATE.get(dev)
