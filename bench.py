@@ -269,7 +269,7 @@ class SweepWorkload:
         self.ops = {h: ShardedSpMM(None, args_for(h), splits=self.splits, local_adj=adj,
                                    make_local=lambda _adj, _args, _h=h: self.plans[_h], chunks=1,
                                    fused=(world > 1 and a.gather == "fused"), use_multicast=not a.no_multicast,
-                                   sync=a.sync) for h in self.sweep}
+                                   sync=a.sync, world=world, rank=rank) for h in self.sweep}
         for h in self.sweep:
             hdl = self.plans[h].sp_info_ptr
             if a.general_kernel:     # force the weighted kernels although the adjacency is value-less (all ones)

@@ -263,9 +263,10 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
     }
     long long seg_nnz = 0;
     for (const Seg &sg : segs) seg_nnz += sg.end - sg.start;
-    // ~16 supertickets per SM, at least 2048 nonzeros (small graphs) and at most 128 K
+    // ~8 supertickets per SM (every warp walks its SM's home list, so the list must stay short; balance comes from
+    // item-level stealing, not from superticket count), at least 2048 nonzeros (small graphs), at most 256 K
     const long long super = g.opt_super_nnz > 0 ? g.opt_super_nnz
-                                                : std::min<long long>(131072, std::max<long long>(2048, (short_nnz + seg_nnz) / std::max(1, g_ctx.sm_count * 16)));
+                                                : std::min<long long>(262144, std::max<long long>(2048, (short_nnz + seg_nnz) / std::max(1, g_ctx.sm_count * 8)));
     std::vector<int4> supers;
     long long n_items = 0;
     if (!segs.empty()) {

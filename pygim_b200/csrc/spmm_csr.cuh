@@ -772,17 +772,26 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
     unsigned smid, nsmid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     asm("mov.u32 %0, %%nsmid;" : "=r"(nsmid));
-    int home = (int)smid, scan_o = 0, scan_u = 0;
+    // the block's warps share how far the SM's home list is already drawn out: a warp that finds a unit exhausted
+    // publishes it, the others skip straight past instead of paying an L2 round trip per exhausted unit
+    __shared__ int s_home_done;
+    if (threadIdx.x == 0) s_home_done = 0;
+    __syncthreads();
+    int home_k = 0, scan_o = 0, scan_u = 0;           // home unit = smid + home_k * nsmid
     unsigned scan_m = 0;
     for (;;) {
         int unit;
-        if (home < n_units) {
-            unit = home;
-            home += (int)nsmid;
+        {   // one lane reads the shared progress (lanes need not be converged here), all lanes take its value
+            int k = home_k;
+            if (lane == 0) k = max(k, *(volatile int *)&s_home_done);
+            home_k = __shfl_sync(FULL, k, 0);
+        }
+        const bool is_home = (int)smid + home_k * (int)nsmid < n_units;
+        if (is_home) {
+            unit = (int)smid + home_k * (int)nsmid;
         } else {
             while (scan_m == 0 && scan_o < n_units) {
-                // nothing left to draw anywhere?  ONE lane reads the counter: lanes that are not converged here (e.g.
-                // inactive column lanes run ahead) must not see different values and part ways around the ballot
+                // nothing left to draw anywhere?  (read by ONE lane, as above)
                 unsigned drawn = 0;
                 if (lane == 0) drawn = *(volatile unsigned int *)(a.warps_out + 1);
                 if (__shfl_sync(FULL, drawn, 0) >= (unsigned)n_units) {
@@ -804,6 +813,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             unit = __shfl_sync(FULL, scan_u, src);
         }
         drain(unit);
+        if (is_home) {          // drain returns only when the unit is drawn out: the block's other warps can skip it
+            if (lane == 0) atomicMax(&s_home_done, home_k + 1);
+            ++home_k;
+        }
     }
     csr_leave<T>(a);
 }

@@ -126,10 +126,13 @@ class ShardedSpMM:
     def __init__(self, adj: Optional[SparseTensor], args, group=None, splits: Optional[Sequence[int]] = None,
                  local_adj: Optional[SparseTensor] = None,
                  make_local: Optional[Callable[[SparseTensor, object], object]] = None, chunks: int = 1,
-                 fused: bool = False, use_multicast: bool = True, sync: str = "flags"):
+                 fused: bool = False, use_multicast: bool = True, sync: str = "flags",
+                 world: Optional[int] = None, rank: Optional[int] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if world is not None:        # e.g. one rank running the whole graph alone inside a multi-rank job
+            self.world, self.rank = int(world), int(rank or 0)
         if splits is None:
             rowptr = adj.csr()[0]
             splits = row_splits_by_nnz(rowptr, self.world) if self.world > 1 else [0, adj.size(0)]
