@@ -263,10 +263,17 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
     }
     long long seg_nnz = 0;
     for (const Seg &sg : segs) seg_nnz += sg.end - sg.start;
-    // ~8 supertickets per SM (every warp walks its SM's home list, so the list must stay short; balance comes from
-    // item-level stealing, not from superticket count), at least 2048 nonzeros (small graphs), at most 256 K
-    const long long super = g.opt_super_nnz > 0 ? g.opt_super_nnz
-                                                : std::min<long long>(262144, std::max<long long>(2048, (short_nnz + seg_nnz) / std::max(1, g_ctx.sm_count * 8)));
+    // Supertickets.  Default: ONE for the segments and ONE for the rows - a single shared queue each, exactly
+    // balanced (measured on a 1/8 Reddit-shape shard and on arxiv-shape: SM-affine lists with stealing cost 50-80 us
+    // of scanning and imbalance per launch, and buy nothing on a graph in arbitrary order).  With a row map (the rows
+    // were reordered for locality) or an explicit super_nnz: ~8 per SM, at least 2048 nonzeros, at most 256 K.
+    long long super = g.opt_super_nnz;
+    if (super <= 0) {
+        if (g.d_row_map != nullptr || !p.hot_super_rows.empty())
+            super = std::min<long long>(262144, std::max<long long>(2048, (short_nnz + seg_nnz) / std::max(1, g_ctx.sm_count * 8)));
+        else
+            super = (1LL << 60);
+    }
     std::vector<int4> supers;
     long long n_items = 0;
     if (!segs.empty()) {
@@ -954,12 +961,13 @@ PYGIM_API int pygim_plan_set_row_map(pygim_handle_t handle, const int32_t *row_m
     CUDA_TRY(cudaSetDevice(g->device));
     CUDA_TRY(cudaDeviceSynchronize());
     if (g->d_row_map) { cudaFree(g->d_row_map); g->d_row_map = nullptr; }
-    if (!row_map) return PYGIM_OK;
+    if (!row_map) return g->parts[0].hot_k == 0 ? replan(g) : PYGIM_OK;
     if (n != g->total_rows) return fail(PYGIM_ERR_INVALID, "row map has %lld entries, the plan has %lld rows", (long long)n, g->total_rows);
     if (g->format == PYGIM_COO && !g->csr_view) return fail(PYGIM_ERR_INVALID, "row maps need a CSR plan or a row-major sorted COO plan");
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g->d_row_map), std::max<size_t>((size_t)n, 1) * sizeof(int)));
     CUDA_TRY(cudaMemcpy(g->d_row_map, row_map, (size_t)n * sizeof(int),
                         mem == PYGIM_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    if (g->parts[0].hot_k == 0) return replan(g);      // a reordered plan schedules SM-affine supertickets
     return PYGIM_OK;
 }
 

@@ -779,8 +779,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
     __syncthreads();
     int home_k = 0, scan_o = 0, scan_u = 0;           // home unit = smid + home_k * nsmid
     unsigned scan_m = 0;
+    // ONE QUEUE (the default plan: no locality to exploit, n_units = segments + rows per column chunk): every warp
+    // drains the units in order - exactly balanced, one atomic per item, nothing to scan.  SM-affine home lists with
+    // stealing are for plans with a locality-preserving row order (row map set), where they pay.
+    const bool one_queue = n_units <= 8;
     for (;;) {
         int unit;
+        if (one_queue) {
+            if (home_k >= n_units) break;
+            drain(home_k++);
+            continue;
+        }
         {   // one lane reads the shared progress (lanes need not be converged here), all lanes take its value
             int k = home_k;
             if (lane == 0) k = max(k, *(volatile int *)&s_home_done);
@@ -790,6 +799,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
         if (is_home) {
             unit = (int)smid + home_k * (int)nsmid;
         } else {
+            // scan the draw counters, 32 at a time, for units that still have undrawn items
             while (scan_m == 0 && scan_o < n_units) {
                 // nothing left to draw anywhere?  (read by ONE lane, as above)
                 unsigned drawn = 0;
