@@ -545,15 +545,33 @@ def run_ours(a):
             c_host = {h: torch.empty((w.r1 - w.r0, h), dtype=w.dtype).pin_memory() for h in sweep}
             c_loc = {h: torch.empty((n, h), dtype=w.dtype, device=dev) for h in sweep}
 
+            s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            order = sorted(sweep, reverse=True)          # widest operand first: its chain is the longest
+
             def step_host():
-                for h in sweep:
-                    mine = xg[h][rank * pad: rank * pad + (b1 - b0)]
-                    mine.copy_(xb_host[h], non_blocking=True)
+                # three streams: uploads of the next operands and downloads of finished results overlap the
+                # all-gather + SpMM of the current one
+                cur = torch.cuda.current_stream(dev)
+                s_in.wait_stream(cur)
+                s_out.wait_stream(cur)
+                up = {}
+                with torch.cuda.stream(s_in):
+                    for h in order:
+                        xg[h][rank * pad: rank * pad + (b1 - b0)].copy_(xb_host[h], non_blocking=True)
+                        up[h] = torch.cuda.Event()
+                        up[h].record(s_in)
+                for h in order:
+                    cur.wait_event(up[h])
                     dist.all_gather_into_tensor(xg[h], xg[h][rank * pad:(rank + 1) * pad])
                     for r in range(world):
                         x_full[h][blk[r]:blk[r + 1]].copy_(xg[h][r * pad: r * pad + blk[r + 1] - blk[r]])
                     w.ops[h].mul(x_full[h], out=c_loc[h], gather=False)
-                    c_host[h].copy_(c_loc[h][w.r0:w.r1], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(cur)
+                    s_out.wait_event(done)
+                    with torch.cuda.stream(s_out):
+                        c_host[h].copy_(c_loc[h][w.r0:w.r1], non_blocking=True)
+                cur.wait_stream(s_out)
                 torch.cuda.synchronize()
             h2d = sum((b1 - b0) * h * esize for h in sweep)
             d2h = sum((w.r1 - w.r0) * h * esize for h in sweep)

@@ -185,11 +185,15 @@ struct Group {
     int64_t last_launches = 0;
 };
 
-static int auto_seg_len(const SparsePart &p) {
-    // ~8 items per resident warp, 512..4096 nonzeros per item (measured on a 1/8 Reddit-shape shard: 512..1024
-    // beats 256 by 8 % - shorter segments cost more partial-sum traffic than they gain in balance)
-    const long long slots = (long long)g_ctx.sm_count * (g_ctx.max_threads_per_sm / 32);
-    long long s = p.nnz / std::max<long long>(1, slots * 8);
+static int auto_seg_len(const SparsePart &p, long long row_bytes) {
+    // A segment costs a release fence, a partial-sum round trip and (for the last arriver) an acquire, so segments
+    // should be as long as balance allows: ~6 items per resident warp of the deep kernel family (16 warps per SM),
+    // twice that for narrow dense rows (<= 128 bytes), 512..4096 nonzeros.  Measured (FLT32, H = 16/32/64/128):
+    // whole Reddit-shape 4096 best (9630 GFLOP/s vs 9390 at 1024); a 1/8 row shard 2048/2048/1024/1024 best
+    // (81/113/208/500 us vs 102/130/225/513 at 512 and 146/169/257/542 at 256).
+    const long long slots = (long long)g_ctx.sm_count * 16;
+    long long s = p.nnz / std::max<long long>(1, slots * 6);
+    if (row_bytes > 0 && row_bytes <= 128) s *= 2;
     long long pow2 = 512;
     while (pow2 < s && pow2 < 4096) pow2 <<= 1;
     return (int)pow2;
@@ -207,6 +211,13 @@ static void free_csr_plan(SparsePart &p) {
     free_plan(p.full);
     for (auto &c : p.chunks) free_plan(c);
     p.chunks.clear();
+}
+
+// bytes of the widest dense tile row a launch of this group gathers
+static long long widest_tile_bytes(const Group &g) {
+    long long w = 0;
+    for (long long c : g.dense_cols) w = std::max(w, c);
+    return w * (long long)dtype_size(g.dtype);
 }
 
 template <typename V> static int upload(V **dst, const std::vector<V> &src) {
@@ -346,7 +357,8 @@ static int build_csr_plan(const Group &g, SparsePart &p, int seg_len) {
 static int replan(Group *g) {
     for (auto &p : g->parts) {
         if (p.h_rowptr.empty()) continue;
-        int rc = build_csr_plan(*g, p, g->opt_seg_len > 0 ? (int)std::min<long long>(g->opt_seg_len, 1 << 30) : auto_seg_len(p));
+        int rc = build_csr_plan(*g, p, g->opt_seg_len > 0 ? (int)std::min<long long>(g->opt_seg_len, 1 << 30)
+                                                        : auto_seg_len(p, widest_tile_bytes(*g)));
         if (rc) return rc;
     }
     return PYGIM_OK;

@@ -112,10 +112,12 @@ def cluster_rows(adj: SparseTensor, n_pivots: Optional[int] = None, seed: int = 
     return perm, stats
 
 
-def auto_seg_len(nnz: int, sm_count: int = 148, threads_per_sm: int = 2048) -> int:
+def auto_seg_len(nnz: int, row_bytes: int = 0, sm_count: int = 148) -> int:
     """The plan's automatic segment length (csrc/backend_pim.cu::auto_seg_len), needed here because rows that will be
     cut into segments must stay all-cold."""
-    s = nnz // max(1, sm_count * (threads_per_sm // 32) * 8)
+    s = nnz // max(1, sm_count * 16 * 6)
+    if 0 < row_bytes <= 128:
+        s *= 2
     p = 512
     while p < s and p < 4096:
         p *= 2
