@@ -756,15 +756,10 @@ def run_sub_workload(a, shape, dev, rank, world, peak, clustered):
     from oracle import oracle as O
     steps, warmup = max(5, min(a.steps, 10)), 3
     rec = {}
-    variants = [("reordered", a.clustered_reorder), ("natural_order", None)] if clustered else [("sharded", None)]
+    variants = [("natural_order", None), ("reordered_cluster", "cluster"), ("reordered_tiles", "tiles")] if clustered \
+        else [("sharded", None)]
     for name, reorder in variants:
         w = SweepWorkload(a, shape, dev, rank, world, clustered=clustered, reorder=reorder)
-        if clustered and reorder:
-            from pygim_b200.backend_pim import pim_ops
-            for h in w.sweep:
-                for k, v in (("cta_threads", a.clustered_cta), ("max_g", a.clustered_max_g)):
-                    if v:
-                        pim_ops.plan_set_option(w.plans[h].sp_info_ptr, k, v)
         w.probe_fused()
         ms, per_h = w.timed(steps, warmup)
         r = {"value": w.flops_step() / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms,
@@ -921,16 +916,12 @@ def main():
                     help="prepare-time row reordering (tiles = cluster + hot/cold shared-memory tiles)")
     ap.add_argument("--hot-k", type=int, default=1280, help="tile rows of the hot/cold plan")
     ap.add_argument("--tile-super-nnz", type=int, default=65536, help="nonzeros per superticket of the hot/cold plan")
-    ap.add_argument("--clustered-reorder", default="tiles", choices=["cluster", "tiles"],
-                    help="how the clustered sub-record is reordered")
     ap.add_argument("--opt", action="append", help="plan option key=value (pygim_plan_set_option), repeatable")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "per-call"],
                     help="N = 1 host-operand step: one pipeline over the sweep (spmm_run_dense_many) or four host calls")
     ap.add_argument("--no-selftest", action="store_true", help="N > 1: skip the whole-matrix multi-GPU self-test")
     ap.add_argument("--no-clustered", action="store_true", help="skip the clustered-graph sub-record (N = 1)")
     ap.add_argument("--no-products", action="store_true", help="skip the products-shape sub-record")
-    ap.add_argument("--clustered-cta", type=int, default=0, help="cta_threads of the reordered clustered plans")
-    ap.add_argument("--clustered-max-g", type=int, default=0, help="max_g of the reordered clustered plans")
     ap.add_argument("--workload", default="spmm", choices=["spmm", "inference"],
                     help="spmm = the headline hidden sweep; inference = 2-layer GCN/GIN/SAGE end to end (configs[3])")
     a = ap.parse_args()

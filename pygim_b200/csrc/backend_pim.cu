@@ -191,9 +191,12 @@ static int auto_seg_len(const SparsePart &p, long long row_bytes) {
     // twice that for narrow dense rows (<= 128 bytes), 512..4096 nonzeros.  Measured (FLT32, H = 16/32/64/128):
     // whole Reddit-shape 4096 best (9630 GFLOP/s vs 9390 at 1024); a 1/8 row shard 2048/2048/1024/1024 best
     // (81/113/208/500 us vs 102/130/225/513 at 512 and 146/169/257/542 at 256).
-    const long long slots = (long long)g_ctx.sm_count * 16;
-    long long s = p.nnz / std::max<long long>(1, slots * 6);
-    if (row_bytes > 0 && row_bytes <= 128) s *= 2;
+    // Short-row graphs run the light family (32 warps per SM) and have few long rows: there balance wins
+    // (products-shape sweep 2670 GFLOP/s at 1024 vs 2510 at 4096).
+    const bool short_rows = p.nnz < 96 * std::max<long long>(p.nrows, 1);
+    const long long slots = (long long)g_ctx.sm_count * (short_rows ? 64 : 16);
+    long long s = p.nnz / std::max<long long>(1, slots * (short_rows ? 8 : 6));
+    if (!short_rows && row_bytes > 0 && row_bytes <= 128) s *= 2;
     long long pow2 = 512;
     while (pow2 < s && pow2 < 4096) pow2 <<= 1;
     return (int)pow2;

@@ -112,11 +112,12 @@ def cluster_rows(adj: SparseTensor, n_pivots: Optional[int] = None, seed: int = 
     return perm, stats
 
 
-def auto_seg_len(nnz: int, row_bytes: int = 0, sm_count: int = 148) -> int:
+def auto_seg_len(nnz: int, row_bytes: int = 0, sm_count: int = 148, nrows: int = 0) -> int:
     """The plan's automatic segment length (csrc/backend_pim.cu::auto_seg_len), needed here because rows that will be
     cut into segments must stay all-cold."""
-    s = nnz // max(1, sm_count * 16 * 6)
-    if 0 < row_bytes <= 128:
+    short = nrows > 0 and nnz < 96 * nrows
+    s = nnz // max(1, sm_count * (64 * 8 if short else 16 * 6))
+    if not short and 0 < row_bytes <= 128:
         s *= 2
     p = 512
     while p < s and p < 4096:
@@ -137,7 +138,7 @@ def hot_cold_plan(adj: SparseTensor, group_of_row: Optional[torch.Tensor] = None
     dev = col.device
     n, m = adj.size(0), adj.size(1)
     nnz = int(col.numel())
-    seg_len = int(seg_len or auto_seg_len(nnz))
+    seg_len = int(seg_len or auto_seg_len(nnz, nrows=n))
     deg = rowptr[1:] - rowptr[:-1]
     short = deg <= seg_len
     w = torch.where(short, deg, torch.zeros_like(deg))
