@@ -160,6 +160,17 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
 PYGIM_API int pygim_spmm_run_group_device(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
                                 void *C, int64_t ldc, void *stream);
 
+/* A BATCH of host-operand SpMMs - the hidden-size sweep of spmm_test.py:119-132 (one prepare + mul per dense size),
+ * or the layers of inference.py:142-149 - as ONE software pipeline: call k runs handles[k] on the host matrix B[k]
+ * ([sum ncols x h_size_k], row stride ldb[k] elements) into the host matrix C[k] (row stride ldc[k]).  All uploads
+ * share one stream and run in the order given, tile by tile (128-byte column tiles); the kernels of a tile start as
+ * soon as it has landed; every finished tile downloads while the next computes.  Per-call entry points expose the
+ * first upload and the last download of EVERY call; the batch exposes one tile's upload and a quarter of one tile's
+ * download in total.  Order the calls by ascending operand size so the kernels start early.  A plan may appear once
+ * per batch.  Returns when every C[k] is complete; pygim_last_timers reports per-call phases as before. */
+PYGIM_API int pygim_spmm_run_many_host(int n_calls, const pygim_handle_t *handles, const void *const *B, const int64_t *ldb,
+                                       void *const *C, const int64_t *ldc);
+
 /* Same computation when the caller already has B as ONE [sum ncols x h_size] device matrix (no
  * dense_split copies): the dense column parts become column tiles of B/C. */
 PYGIM_API int pygim_spmm_device(pygim_handle_t handle, const void *B, int64_t ldb, void *C, int64_t ldc, void *stream);

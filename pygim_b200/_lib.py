@@ -21,7 +21,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 SYMBOLS = [
     "pygim_last_error", "pygim_abi_version", "pygim_dpu_init_ranks", "pygim_dpu_init_dpus", "pygim_dpu_release",
     "pygim_device_info", "pygim_spmm_to_device_group", "pygim_spmm_free_group", "pygim_plan_set_option",
-    "pygim_plan_stats", "pygim_spmm_run_group_host", "pygim_spmm_run_group_device", "pygim_spmm_device", "pygim_spmm_device_peers",
+    "pygim_plan_stats", "pygim_spmm_run_group_host", "pygim_spmm_run_many_host", "pygim_spmm_run_group_device", "pygim_spmm_device", "pygim_spmm_device_peers",
     "pygim_last_timers", "pygim_last_launches", "pygim_partition_rows_by_nnz", "pygim_partition_rows_even",
     "pygim_plan_layout", "pygim_plan_set_row_map", "pygim_spmm_device_ex", "pygim_wait_flags", "pygim_quantize", "pygim_plan_set_hot_tiles",
 ]
@@ -58,6 +58,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pygim_plan_set_option.argtypes = [C.c_uint64, C.c_char_p, i64]
     lib.pygim_plan_stats.argtypes = [C.c_uint64, ci, P(i64)]
     lib.pygim_spmm_run_group_host.argtypes = [C.c_uint64, ci, P(vp), P(i64), vp, i64]
+    lib.pygim_spmm_run_many_host.argtypes = [ci, P(C.c_uint64), P(vp), P(i64), P(vp), P(i64)]
     lib.pygim_spmm_run_group_device.argtypes = [C.c_uint64, ci, P(vp), P(i64), vp, i64, vp]
     lib.pygim_spmm_device.argtypes = [C.c_uint64, vp, i64, vp, i64, vp]
     lib.pygim_spmm_device_peers.argtypes = [C.c_uint64, vp, i64, P(vp), ci, vp, i64, i64, vp]

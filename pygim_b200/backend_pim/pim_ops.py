@@ -81,7 +81,6 @@ def dpu_release() -> None:
     are never reused, so a front-end object that outlives the release just holds an unknown handle."""
     for h in list(_GROUPS):
         spmm_free_group(h)
-    _MANY_STATE.clear()
     _lib.check(_lib.lib().pygim_dpu_release())
     _STATE.update(initialised=False, nr_ranks=0)
 
@@ -441,56 +440,37 @@ def quantize(x: torch.Tensor, dtype: torch.dtype):
     return scale, xq
 
 
-_MANY_STATE: dict = {}
-
-
 def spmm_run_dense_many(handles: Sequence[int], Bs: Sequence[torch.Tensor], outs: Sequence[torch.Tensor]) -> None:
-    """Several host-operand SpMMs (e.g. one per hidden size, or per layer) as ONE software pipeline: the upload of
-    operand k+1 and the download of result k-1 overlap the kernels of call k (three streams, one sync at the end).
+    """Several host-operand SpMMs (one per hidden size of spmm_test.py's sweep, or per layer) as ONE software
+    pipeline (pygim_spmm_run_many_host): uploads run tile by tile in one stream, smallest operand first so the
+    kernels start after a fraction of a millisecond; every finished tile downloads while the next computes.
     `Bs` / `outs` are host tensors (pinned for full PCIe rate); results are complete when the call returns.  The
     per-call host entry point (spmm_run_dense with a host operand) exposes the first upload and the last download of
-    EVERY call; this exposes them once per batch."""
+    EVERY call; this exposes one tile's upload and a fraction of one tile's download per batch."""
     assert len(handles) == len(Bs) == len(outs)
-    # largest operand first: its upload, kernel and download are the longest chain, so it must not be the last to
-    # start (the results are independent, the order is free)
-    order = sorted(range(len(handles)), key=lambda k: -Bs[k].numel())
-    handles, Bs, outs = [handles[k] for k in order], [Bs[k] for k in order], [outs[k] for k in order]
-    metas = [_meta(h) for h in handles]
-    dev = metas[0].device
-    st = _MANY_STATE.get(dev)
-    if st is None:
-        st = {"in": torch.cuda.Stream(dev), "out": torch.cuda.Stream(dev), "cmp": torch.cuda.Stream(dev), "buf": {}}
-        _MANY_STATE[dev] = st
-    cur = torch.cuda.current_stream(dev)
-    for s in (st["in"], st["cmp"], st["out"]):
-        s.wait_stream(cur)
-    staged = []
-    for h, m, B, out in zip(handles, metas, Bs, outs):
+    if not handles:
+        return
+    order = sorted(range(len(handles)), key=lambda k: Bs[k].numel())
+    hs, bs, cs, ldbs, ldcs, keep = [], [], [], [], [], []
+    for k in order:
+        m, B, out = _meta(handles[k]), Bs[k], outs[k]
         if B.is_cuda or out.is_cuda:
             raise _lib.PygimError("spmm_run_dense_many takes host operands")
-        key = (int(h), tuple(B.shape), B.dtype)
-        if key not in st["buf"]:
-            st["buf"][key] = (torch.empty(B.shape, dtype=B.dtype, device=dev),
-                              torch.empty((m.total_rows, m.h_size), dtype=m.dtype, device=dev))
-        staged.append(st["buf"][key])
-    ev_in = []
-    with torch.cuda.stream(st["in"]):
-        for (Bd, _), B in zip(staged, Bs):
-            Bd.copy_(B, non_blocking=True)
-            e = torch.cuda.Event()
-            e.record(st["in"])
-            ev_in.append(e)
-    for k, (h, (Bd, Cd), out) in enumerate(zip(handles, staged, outs)):
-        st["cmp"].wait_event(ev_in[k])
-        with torch.cuda.stream(st["cmp"]):
-            spmm_run_dense(h, Bd, out=Cd)
-            e = torch.cuda.Event()
-            e.record(st["cmp"])
-        st["out"].wait_event(e)
-        with torch.cuda.stream(st["out"]):
-            out.copy_(Cd, non_blocking=True)
-    st["out"].synchronize()
-    cur.wait_stream(st["cmp"])
+        if B.dtype != m.dtype or B.dim() != 2 or B.size(1) != m.h_size or B.size(0) != m.total_cols:
+            raise _lib.PygimError("dense operand %d has shape %s/%s, expected (%d, %d) %s"
+                                  % (k, tuple(B.shape), B.dtype, m.total_cols, m.h_size, m.dtype))
+        if B.stride(1) != 1 and B.numel():
+            B = B.contiguous()
+        keep.append(B)
+        out = _check_out(out, m, B)
+        hs.append(int(handles[k]))
+        bs.append(B.data_ptr())
+        cs.append(out.data_ptr())
+        ldbs.append(B.stride(0) if B.size(0) > 1 else max(B.size(1), 1))
+        ldcs.append(out.stride(0) if out.size(0) > 1 else max(m.h_size, 1))
+    n = len(hs)
+    _lib.check(_lib.lib().pygim_spmm_run_many_host(n, (C.c_uint64 * n)(*hs), (C.c_void_p * n)(*bs), _i64_array(ldbs),
+                                                   (C.c_void_p * n)(*cs), _i64_array(ldcs)))
 
 
 def _grande_reassemble(m: _GroupMeta, B_parts: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -114,6 +114,9 @@ struct CsrPlan {
     int *d_long_seg_ptr = nullptr;
     int n_items = 0, n_super = 0, n_seg_super = 0;
     int n_seg = 0, n_long = 0;
+    int n_slots = 0;          // rows of the partial-sum scratch (pieces of rows cut into several segments)
+    bool tiny_split = false;  // two-launch family: rows of <= kTinyRow nonzeros are NOT in this plan (csr_tiny_rows_kernel
+                              // takes them), every other row is a list of seg_len-bounded pieces, longest first
 };
 
 struct SparsePart {
@@ -185,7 +188,16 @@ struct Group {
     int64_t last_launches = 0;
 };
 
-static int auto_seg_len(const SparsePart &p, long long row_bytes) {
+// Kernel family of a sparse part: 0 deep (128 registers, 16 gathers in flight) for long rows; 3 light (64 registers,
+// twice the warps) for short rows; 4 the two-launch family for very short rows (citation graphs: most rows have a
+// handful of nonzeros and go to csr_tiny_rows_kernel); 1 high occupancy and 2 streamed row items stay selectable.
+static int kernel_family(const Group &g, const SparsePart &p) {
+    if (g.opt_short_rows >= 0) return (int)g.opt_short_rows;
+    const long long rows1 = std::max<long long>(p.nrows, 1);
+    return p.nnz < 12 * rows1 ? 4 : (p.nnz < 96 * rows1 ? 3 : 0);
+}
+
+static int auto_seg_len(const Group &g, const SparsePart &p, long long row_bytes) {
     // A segment costs a release fence, a partial-sum round trip and (for the last arriver) an acquire, so segments
     // should be as long as balance allows: ~6 items per resident warp of the deep kernel family (16 warps per SM),
     // twice that for narrow dense rows (<= 128 bytes), 512..4096 nonzeros.  Measured (FLT32, H = 16/32/64/128):
@@ -193,6 +205,9 @@ static int auto_seg_len(const SparsePart &p, long long row_bytes) {
     // (81/113/208/500 us vs 102/130/225/513 at 512 and 146/169/257/542 at 256).
     // Short-row graphs run the light family (32 warps per SM) and have few long rows: there balance wins
     // (products-shape sweep 2670 GFLOP/s at 1024 vs 2510 at 4096).
+    // The two-launch family is latency-bound (a launch is a few waves of dependent chains): no piece longer than
+    // four gather rounds of one warp.
+    if (kernel_family(g, p) == 4 && p.hot_super_rows.empty()) return 256;
     const bool short_rows = p.nnz < 96 * std::max<long long>(p.nrows, 1);
     const long long slots = (long long)g_ctx.sm_count * (short_rows ? 64 : 16);
     long long s = p.nnz / std::max<long long>(1, slots * (short_rows ? 8 : 6));
@@ -254,9 +269,25 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
     }
     const int max_rows = (int)std::max<long long>(1, std::min<long long>(31, g.opt_rows_per_ticket > 0 ? g.opt_rows_per_ticket : 31));
     long long short_nnz = 0;
+    const bool tiny_split = kernel_family(g, p) == 4 && p.hot_super_rows.empty();
+    out.tiny_split = tiny_split;
+    int n_slots = 0;
     for (long long r = r0; r < r1; ++r) {
         const long long s = (unsigned)rp[r], e = (unsigned)rp[r + 1];
         const long long n = e - s;
+        if (tiny_split && n <= seg_len) {
+            // rows of at most kTinyRow nonzeros belong to csr_tiny_rows_kernel; every other uncut row is ONE piece
+            // that stores its row directly (long_idx = ~row: no partial sum, no merge)
+            if (n > (long long)pygim::kTinyRow) {
+                Seg sg;
+                sg.long_idx = ~(int)(r - r0);
+                sg.start = (int)s;
+                sg.end = (int)e;
+                sg.slot = 0;
+                segs.push_back(sg);
+            }
+            continue;
+        }
         if (n > seg_len) {
             const long long k = (n + seg_len - 1) / seg_len;
             // equal pieces rounded up to a multiple of 32 so every piece but the last runs full rounds
@@ -266,11 +297,11 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
                 sg.long_idx = (int)long_rows.size();
                 sg.start = (int)b;
                 sg.end = (int)std::min(e, b + piece);
-                sg.slot = (int)segs.size();
+                sg.slot = n_slots++;
                 segs.push_back(sg);
             }
             long_rows.push_back((int)(r - r0));
-            long_ptr.push_back((int)segs.size());
+            long_ptr.push_back(n_slots);
         } else {
             short_nnz += n;
         }
@@ -307,7 +338,7 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
         }
     }
     out.n_seg_super = (int)supers.size();
-    {
+    if (!tiny_split) {
         long long acc = 0, first = r0;
         size_t next_cut = 1;               // hot/cold plans: the caller's superticket boundaries
         const bool fixed = !p.hot_super_rows.empty() && r0 == 0 && r1 == p.nrows;
@@ -333,6 +364,7 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
     out.n_items = (int)std::min<long long>(n_items, 0x7fffffff);
     out.n_super = (int)supers.size();
     out.n_seg = (int)segs.size();
+    out.n_slots = n_slots;
     out.n_long = (int)long_rows.size();
     int rc;
     if ((rc = upload(&out.d_supers, supers))) return rc;
@@ -361,7 +393,7 @@ static int replan(Group *g) {
     for (auto &p : g->parts) {
         if (p.h_rowptr.empty()) continue;
         int rc = build_csr_plan(*g, p, g->opt_seg_len > 0 ? (int)std::min<long long>(g->opt_seg_len, 1 << 30)
-                                                        : auto_seg_len(p, widest_tile_bytes(*g)));
+                                                        : auto_seg_len(*g, p, widest_tile_bytes(*g)));
         if (rc) return rc;
     }
     return PYGIM_OK;
@@ -551,7 +583,7 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         const size_t n_counters = 4 + (size_t)pl.n_super * chunks + (size_t)pl.n_long * chunks;
         Scratch scratch;
         Scratch *sc = &scratch;
-        int rc = get_scratch(g, stream, n_counters, (size_t)pl.n_seg * (size_t)ldp * s, false, sc);
+        int rc = get_scratch(g, stream, n_counters, (size_t)pl.n_slots * (size_t)ldp * s, false, sc);
         if (rc) return rc;
         CsrLaunch l;
         l.rowptr = p.csr_rowptr() + pl.row_begin;
@@ -574,12 +606,10 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
         l.nrows = (int)(pl.row_end - pl.row_begin);
         l.seg_len = p.seg_len;
         l.nnz_total = p.nnz;
-        // kernel family: 0 deep (128 registers, 16 gathers in flight) for long rows; 3 light (64 registers, twice the
-        // warps) for short rows; 4 one lane group per row for very short rows (citation graphs); 1 high occupancy
-        // and 2 streamed row items stay selectable
-        const long long rows1 = std::max<long long>(p.nrows, 1);
-        l.short_rows = g->opt_short_rows >= 0 ? (int)g->opt_short_rows
-                                              : (p.nnz < 12 * rows1 ? 4 : (p.nnz < 96 * rows1 ? 3 : 0));
+        {   // the family is part of the plan (kernel_family); a plan without the tiny-row split runs family 4 as 3
+            const int family = kernel_family(*g, p);
+            l.short_rows = pl.tiny_split ? 4 : (family == 4 ? 3 : family);
+        }
         l.max_g = max_g;
         l.cta_threads = g->opt_cta_threads > 0 ? (int)g->opt_cta_threads : 256;
         if (p.hot_k > 0) {
@@ -916,6 +946,7 @@ PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int6
     } else if (!std::strcmp(key, "unit_values")) {
         g->opt_unit_values = value;
     } else if (!std::strcmp(key, "short_rows")) {
+        if (g->opt_short_rows != value && !(g->parts.empty() || g->parts[0].hot_k > 0)) rebuild = true;   // the family shapes the plan
         g->opt_short_rows = value;
     } else if (!std::strcmp(key, "host_chunks")) {
         g->opt_host_chunks = value;
@@ -1113,11 +1144,15 @@ PYGIM_API int pygim_wait_flags(const int32_t *flags, int n, int32_t epoch, void 
 //   * the LAST tile (or the only one) is additionally cut into nnz-balanced row chunks (CSR) so that its download
 //     overlaps its own kernels and only the last chunk's copy is exposed.
 // Each tile is staged contiguously on the device ([rowsB x tile_width]), so it is L2 friendly for the gathers.
-PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
-                              void *C, int64_t ldc) {
-    Group *g = as_group(handle);
-    if (!g) return PYGIM_ERR_INVALID;
-    if (!B_parts || !ldb || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
+// Enqueue one host-operand SpMM as a three-stream software pipeline: column tile t+1 uploads on `sin` and the
+// finished rows of tile t-1 download on `sout` while tile t computes on `st`.  Nothing is awaited: the caller joins
+// `sout` into `st` and synchronises - once per call (pygim_spmm_run_group_host) or once per batch of calls
+// (pygim_spmm_run_many_host, where the uploads of call k+1 overlap the kernels of call k as well).
+// `chunk_last`: cut the LAST tile's launch into nnz-balanced row chunks whose downloads follow chunk by chunk, so
+// only a fraction of one tile's download is exposed at the end (in a batch: the last call only - every other
+// download already overlaps the kernels that follow it, and a chunked tile costs three extra launches).
+static int host_enqueue(Group *g, int n_ds, const void *const *B_parts, const int64_t *ldb, void *C, int64_t ldc,
+                        cudaStream_t st, cudaStream_t sin, cudaStream_t sout, bool first_of_batch, bool chunk_last) {
     if (n_ds != (int)g->dense_cols.size())
         return fail(PYGIM_ERR_INVALID, "expected %d dense parts, got %d", (int)g->dense_cols.size(), n_ds);
     CUDA_TRY(cudaSetDevice(g->device));
@@ -1164,7 +1199,7 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
 
     // ---- row chunks of the last tile (CSR only: COO chunks are nnz ranges, not row ranges)
     int n_chunks = 1;
-    if (pipelined && (g->format == PYGIM_CSR || g->csr_view) && !g->d_row_map && g->parts[0].hot_k == 0 &&
+    if (chunk_last && pipelined && (g->format == PYGIM_CSR || g->csr_view) && !g->d_row_map && g->parts[0].hot_k == 0 &&
         g->parts[0].nnz >= 4096 && rowsC >= 64) {
         n_chunks = g->opt_host_chunks > 0 ? (int)g->opt_host_chunks : 4;
         if (g->parts[0].chunks.size() != (size_t)n_chunks) {
@@ -1181,20 +1216,17 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
             }
         }
     }
-    if (!g->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
-    if (!g->copy_in_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_in_stream, cudaStreamNonBlocking));
-    while (g->chunk_done.size() < tiles.size() * 2 + (size_t)n_chunks + 2) {
+    while (g->chunk_done.size() < tiles.size() * (size_t)(n_chunks + 1) + 4) {
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         g->chunk_done.push_back(e);
     }
-    cudaStream_t st = cudaStreamPerThread, sin = g->copy_in_stream, sout = g->copy_stream;
     size_t next_event = 0;
     auto new_event = [&]() { return g->chunk_done[next_event++]; };
 
     g->last_launches = 0;
     CUDA_TRY(cudaEventRecord(g->ev[0], st));
-    {   // the copy streams start after everything already queued on the compute stream
+    if (first_of_batch) {   // the copy streams start after everything already queued on the compute stream
         cudaEvent_t e = new_event();
         CUDA_TRY(cudaEventRecord(e, st));
         CUDA_TRY(cudaStreamWaitEvent(sin, e, 0));
@@ -1218,7 +1250,7 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
         CUDA_TRY(cudaStreamWaitEvent(st, uploaded[t], 0));
         if (t == 0) CUDA_TRY(cudaEventRecord(g->ev[1], st));          // first tile on the device: kernels start
         const bool last = t + 1 == tiles.size();
-        const int chunks_here = last ? n_chunks : 1;
+        const int chunks_here = (last && chunk_last) ? n_chunks : 1;
         for (int k = 0; k < chunks_here; ++k) {
             long long brow = 0;
             for (size_t i = 0; i < g->parts.size(); ++i) {            // sparse part 0 overwrites, parts >= 1 add
@@ -1245,8 +1277,13 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
                                            cudaMemcpyDeviceToHost, sout));
         }
     }
-    {   // join the copy streams; ev[3] = last download done
-        cudaEvent_t e = new_event();
+    return PYGIM_OK;
+}
+
+// join the download stream into the compute stream, wait, and read the phase timers of `g` (ev[3] = last download done)
+static int host_join(Group *g, cudaStream_t st, cudaStream_t sout) {
+    {
+        cudaEvent_t e = g->chunk_done.back();          // host_enqueue keeps spare events at the end
         CUDA_TRY(cudaEventRecord(e, sout));
         CUDA_TRY(cudaStreamWaitEvent(st, e, 0));
         CUDA_TRY(cudaEventRecord(g->ev[3], st));
@@ -1258,6 +1295,78 @@ PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const v
     CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->timers_ms[2] = ms;   // kernels (uploads/downloads overlap)
     CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[2], g->ev[3])); g->timers_ms[3] = ms;   // exposed tail of the download
     g->timers_ms[4] = 0;   // alignment: none
+    return PYGIM_OK;
+}
+
+static int host_streams(Group *g) {
+    if (!g->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    if (!g->copy_in_stream) CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_in_stream, cudaStreamNonBlocking));
+    return PYGIM_OK;
+}
+
+PYGIM_API int pygim_spmm_run_group_host(pygim_handle_t handle, int n_ds, const void *const *B_parts, const int64_t *ldb,
+                              void *C, int64_t ldc) {
+    Group *g = as_group(handle);
+    if (!g) return PYGIM_ERR_INVALID;
+    if (!B_parts || !ldb || !C) return fail(PYGIM_ERR_INVALID, "null buffer");
+    CUDA_TRY(cudaSetDevice(g->device));
+    int rc = host_streams(g);
+    if (rc) return rc;
+    cudaStream_t st = cudaStreamPerThread;
+    rc = host_enqueue(g, n_ds, B_parts, ldb, C, ldc, st, g->copy_in_stream, g->copy_stream, true, true);
+    if (rc) {
+        (void)cudaStreamSynchronize(g->copy_in_stream);   // never return with copies from the caller's buffers in flight
+        (void)cudaStreamSynchronize(g->copy_stream);
+        (void)cudaStreamSynchronize(st);
+        return rc;
+    }
+    return host_join(g, st, g->copy_stream);
+}
+
+PYGIM_API int pygim_spmm_run_many_host(int n_calls, const pygim_handle_t *handles, const void *const *B, const int64_t *ldb,
+                                       void *const *C, const int64_t *ldc) {
+    if (n_calls <= 0) return PYGIM_OK;
+    if (!handles || !B || !ldb || !C || !ldc) return fail(PYGIM_ERR_INVALID, "null argument");
+    std::vector<Group *> gs((size_t)n_calls);
+    for (int k = 0; k < n_calls; ++k) {
+        gs[(size_t)k] = as_group(handles[k]);
+        if (!gs[(size_t)k]) return PYGIM_ERR_INVALID;
+        if (!B[k] || !C[k]) return fail(PYGIM_ERR_INVALID, "null buffer (call %d)", k);
+        if (gs[(size_t)k]->device != gs[0]->device) return fail(PYGIM_ERR_INVALID, "all plans of a batch must live on one device");
+        for (int j = 0; j < k; ++j)
+            if (gs[(size_t)j] == gs[(size_t)k]) return fail(PYGIM_ERR_INVALID, "a plan may appear once per batch (its staging buffers are per plan)");
+    }
+    CUDA_TRY(cudaSetDevice(gs[0]->device));
+    int rc = host_streams(gs[0]);
+    if (rc) return rc;
+    // ONE upload stream and ONE download stream for the whole batch: PCIe transfers run in the order given
+    cudaStream_t st = cudaStreamPerThread, sin = gs[0]->copy_in_stream, sout = gs[0]->copy_stream;
+    for (int k = 0; k < n_calls && !rc; ++k) {
+        Group *g = gs[(size_t)k];
+        std::vector<const void *> parts;
+        std::vector<long long> lds;
+        column_tiles(g, B[k], ldb[k], parts, lds);
+        std::vector<int64_t> l64(lds.begin(), lds.end());
+        rc = host_enqueue(g, (int)parts.size(), parts.data(), l64.data(), C[k], ldc[k], st, sin, sout, k == 0, k + 1 == n_calls);
+    }
+    if (rc) {
+        (void)cudaStreamSynchronize(sin);
+        (void)cudaStreamSynchronize(sout);
+        (void)cudaStreamSynchronize(st);
+        return rc;
+    }
+    rc = host_join(gs[(size_t)n_calls - 1], st, sout);
+    if (rc) return rc;
+    // phase timers of the earlier calls: their events have all completed
+    for (int k = 0; k + 1 < n_calls; ++k) {
+        Group *g = gs[(size_t)k];
+        float ms = 0;
+        g->timers_ms[0] = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[0], g->ev[1])); g->timers_ms[1] = ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g->ev[1], g->ev[2])); g->timers_ms[2] = ms;
+        g->timers_ms[3] = 0;
+        g->timers_ms[4] = 0;
+    }
     return PYGIM_OK;
 }
 

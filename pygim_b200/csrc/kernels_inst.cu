@@ -112,7 +112,19 @@ static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t
         if (l.short_rows == 1) return launch_csr_t<E, G, UNIT, CsrTuneShort<E, UNIT>>(a, l, launches);
     }
     if (l.short_rows == 3) return launch_csr_t<E, G, UNIT, CsrTuneLight<E, UNIT>>(a, l, launches);
-    if (l.short_rows == 4) return launch_csr_t<E, G, UNIT, CsrTuneLight<E, UNIT>, 2>(a, l, launches);   // lane group per row
+    if (l.short_rows == 4) {
+        // tiny rows (<= kTinyRow nonzeros) by a matrix-wide grid of lane groups, the rest by the persistent kernel
+        // (which skips the tiny rows); the launches write disjoint rows
+        const int col_chunks = (a.nvec + G - 1) / G;
+        if (a.nrows > 0) {
+            const unsigned bx = (unsigned)((a.nrows + (256 / G) - 1) / (256 / G));
+            csr_tiny_rows_kernel<T, E, G, UNIT><<<dim3(bx, (unsigned)col_chunks), 256, 0, l.stream>>>(a);
+            ++*launches;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+        return launch_csr_t<E, G, UNIT, CsrTuneLight<E, UNIT>, 2>(a, l, launches);
+    }
     return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>>(a, l, launches);
 }
 
@@ -194,7 +206,7 @@ template <int E> static cudaError_t launch_csr_e(const CsrLaunch &l, int64_t *la
         a.epi.peers[p] = p < l.epi.n_peers ? l.epi.peers[p] : nullptr;
         a.epi.flags[p] = p < l.epi.n_peers ? l.epi.flags[p] : nullptr;
     }
-    if (l.n_items == 0 || a.nvec == 0) return cudaSuccess;
+    if ((l.n_items == 0 && l.short_rows != 4) || a.nvec == 0) return cudaSuccess;   // family 4: the tiny-row launch has no items
     cudaError_t err;
     if (l.hot_k > 0) {
         if constexpr (sizeof(T) * E == 16) {

@@ -40,11 +40,13 @@ namespace pygim {
 constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
 
 struct Seg {       // one nnz-bounded piece of a long row
-    int long_idx;  // which long row (index into long_rows / long_seg_ptr)
+    int long_idx;  // which long row (index into long_rows / long_seg_ptr); < 0: the piece is the WHOLE row ~long_idx
     int start;     // first nonzero (index into colind/val)
     int end;       // one past the last nonzero
     int slot;      // row of the partial buffer this piece writes (slots of one row are consecutive)
 };
+
+static_assert(sizeof(Seg) == 16, "segment descriptors are read as one 16-byte word");
 
 // what the row store does besides writing the sum (all optional, all decided per launch)
 struct Epilogue {
@@ -580,87 +582,100 @@ __device__ __forceinline__ void csr_stream_rows(const CsrArgs<T> &a, int first, 
     }
 }
 
-// SHORT ROWS, lean path: one LANE GROUP per row.  The P = 32/G lane groups of a warp take P consecutive rows of the
-// item at a time; a group walks its own row nonzero by nonzero (index load broadcast inside the group, one 16-byte
-// gather per lane, UQ nonzeros in flight), so a row's sum never leaves its group: no shuffle tree, no alignment
-// prologue, no per-row loop setup - about 2 warp instructions per nonzero instead of ~230 per ROW on the
-// warp-wide path (arxiv-shape, mean degree 7: 34 -> 3 instructions per nonzero).  Rows longer than `wide_from`
-// would leave the other groups idle; they are returned as a bit mask and processed warp-wide by the caller.
-template <typename T, int E, int G, int UQ, bool UNIT>
-__device__ __forceinline__ unsigned csr_rows_by_group(const CsrArgs<T> &a, int first, int count, int rp, int chunk,
-                                                      int wide_from) {
+// TINY ROWS (graphs of mean degree < ~12: citation networks): a launch of its own, one LANE GROUP per row.
+// On arxiv-shape 92 % of the rows have at most 8 nonzeros; walking each of them with a whole warp costs a dependent
+// chain (row bounds -> indices -> gathers -> shuffle tree -> store) of ~230 instructions and three memory latencies
+// per ROW, and a persistent grid serialises those chains per warp (measured: 69 us per launch for 8 us of memory
+// traffic).  Here the grid is as wide as the matrix: every group of G lanes owns one row, reads its (at most W)
+// column indices at once (the same address across the group: one broadcast transaction), gathers one 16-byte word
+// per lane and nonzero and stores its row: no tickets, no shuffles, ~3 instructions per
+// nonzero, 64 resident warps per SM, every row of the matrix in flight within a few waves.  Rows longer than W are
+// left to the persistent kernel (STREAM == 2 skips the rows taken here); the two launches write disjoint rows.
+constexpr int kTinyRow = 8;       // longest row a lane group takes
+template <typename T, int E, int G, bool UNIT>
+__global__ void __launch_bounds__(256, (E >= 8) ? 4 : 8) csr_tiny_rows_kernel(const __grid_constant__ CsrArgs<T> a) {
     using Acc = typename Arith<T>::Acc;
     using Shfl = typename Arith<T>::Shfl;
-    constexpr int P = 32 / G;
-    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int W = kTinyRow;
     const int lane = threadIdx.x & 31;
-    const int sub = lane / G;
-    const int vec = chunk * G + (lane % G);
-    const bool active = vec < a.nvec;
+    const int row = blockIdx.x * (256 / G) + (int)threadIdx.x / G;
+    const int vec = blockIdx.y * G + (lane % G);
+    if (row >= a.nrows || vec >= a.nvec) return;
+    const int i = __ldg(a.rowptr + row);
+    const int n = __ldg(a.rowptr + row + 1) - i;
+    if (n > W) return;
     const T *Bcol = a.B + (long long)vec * E;
-    asm volatile("" : "+l"(Bcol));
-    const int deg = __shfl_down_sync(FULL, rp, 1) - rp;
-    const unsigned wide = __ballot_sync(FULL, lane < count && deg > wide_from);
-    for (int j0 = 0; j0 < count; j0 += P) {
-        const int j = j0 + sub;
-        const int jj = min(j, count - 1);
-        int i = __shfl_sync(FULL, rp, jj);
-        int end = __shfl_sync(FULL, rp, jj + 1);
-        const bool mine = j < count && !((wide >> jj) & 1u) && active;
-        if (!mine) end = i;
-        Acc acc[E];
+    Acc acc[E];
 #pragma unroll
-        for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
-        while (i < end) {
-            int c[UQ];
-            Shfl v[UQ];
+    for (int k = 0; k < E; ++k) acc[k] = (Acc)0;
+    // two halves of W/2 nonzeros: the second half's indices (rows of 5..8 nonzeros only) load while the first
+    // half's gathers are in flight
+    constexpr int HW = W / 2;
+    int c[HW], c2[HW];
+    Shfl v[HW], v2[HW];
 #pragma unroll
-            for (int u = 0; u < UQ; ++u) {
-                c[u] = 0;
-                v[u] = (Shfl)1;
-                if (i + u < end) {
-                    c[u] = ld_stream(a.colind + i + u);
-                    if constexpr (!UNIT) v[u] = ld_stream(a.val + i + u);
-                }
-            }
-            Pack<T, E> b[UQ];
-#pragma unroll
-            for (int u = 0; u < UQ; ++u)
-                if (i + u < end) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, c[u], a.ldb_bytes));
-#pragma unroll
-            for (int u = 0; u < UQ; ++u)
-                if (i + u < end) fma_pack<T, E>(acc, b[u], v[u]);
-            i += UQ;
+    for (int u = 0; u < HW; ++u) {
+        c[u] = 0;
+        v[u] = (Shfl)1;
+        if (u < n) {
+            c[u] = ld_stream(a.colind + i + u);
+            if constexpr (!UNIT) v[u] = ld_stream(a.val + i + u);
         }
-        if (mine) csr_emit<T, E>(a, acc, first + j, vec);
     }
-    return wide;
+    Pack<T, E> b[HW];
+#pragma unroll
+    for (int u = 0; u < HW; ++u)
+        if (u < n) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, c[u], a.ldb_bytes));
+    if (n > HW) {
+#pragma unroll
+        for (int u = 0; u < HW; ++u) {
+            c2[u] = 0;
+            v2[u] = (Shfl)1;
+            if (HW + u < n) {
+                c2[u] = ld_stream(a.colind + i + HW + u);
+                if constexpr (!UNIT) v2[u] = ld_stream(a.val + i + HW + u);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < HW; ++u)
+        if (u < n) fma_pack<T, E>(acc, b[u], v[u]);
+    if (n > HW) {
+#pragma unroll
+        for (int u = 0; u < HW; ++u)
+            if (HW + u < n) b[u] = ld_dense<T, E>(row_ptr<T>(Bcol, c2[u], a.ldb_bytes));
+#pragma unroll
+        for (int u = 0; u < HW; ++u)
+            if (HW + u < n) fma_pack<T, E>(acc, b[u], v2[u]);
+    }
+    csr_emit<T, E>(a, acc, row, vec);
 }
 
 // ---------------------------------------------------------------------------------------------- scheduling
 struct CsrItem {
-    int long_idx;      // segment: its long row; rows: -1
-    int first;         // segment: slot of the partial buffer; rows: first row of the item
+    int first;         // rows: first row of the item (from the ticket by arithmetic)
     int count;         // rows covered (1 for a segment)
-    int rp;            // rows: lane l holds rowptr[first + l] (l <= count); segment: lane 0 start, other lanes end
+    int4 w;            // LOADED, and not touched before the item is processed (so the load stays asynchronous):
+                       //   rows:    w.x = this lane's rowptr entry, lane l holds rowptr[first + l] (l <= count)
+                       //   segment: the Seg descriptor (long_idx, start, end, slot)
 };
 
 // Item `it` of superticket `sp`.  Its address follows from the ticket by arithmetic alone: ONE dependent load
-// (rowptr entries, or the segment descriptor) between drawing a ticket and having the item.
+// (rowptr entries, or the segment descriptor as one 16-byte word) between drawing a ticket and having the item.
+// Nothing here consumes the loaded registers: any arithmetic on them would make the warp wait for the load right
+// here instead of after the previous item's work (measured on arxiv-shape: two overlapping scalar loads into one
+// register cost a full memory latency per item, 29 % of all stall samples).
 template <typename T> __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, const int4 &sp, int it) {
     CsrItem r;
     const int lane = threadIdx.x & 31;
     if (sp.x < 0) {
-        const Seg sg = a.segs[~sp.x + it];
-        r.long_idx = sg.long_idx;
-        r.first = sg.slot;
+        r.first = 0;
         r.count = 1;
-        r.rp = lane == 0 ? sg.start : sg.end;
+        r.w = __ldg(reinterpret_cast<const int4 *>(a.segs + (~sp.x + it)));
     } else {
-        r.long_idx = -1;
         r.first = sp.x + it * sp.z;
         r.count = min(sp.z, sp.x + sp.y - r.first);
-        r.rp = a.rowptr[min(r.first + lane, a.nrows)];
+        r.w.x = a.rowptr[min(r.first + lane, a.nrows)];
     }
     return r;
 }
@@ -699,36 +714,31 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
     const int lane = threadIdx.x & 31;
     const int n_units = a.n_super * a.col_chunks;
 
-    auto process = [&](const CsrItem &cur, int chunk) {
-        if (STREAM == 2 && cur.long_idx < 0) {
-            // one lane group per row; rows too long for that (but not segmented) warp-wide afterwards
-            unsigned wide = csr_rows_by_group<T, E, G, 4, UNIT>(a, cur.first, cur.count, cur.rp, chunk, 8 * (32 / G) + 32);
-            while (wide) {
-                const int j = __ffs(wide) - 1;
-                wide &= wide - 1;
-                const int start = __shfl_sync(FULL, cur.rp, j);
-                const int end = __shfl_sync(FULL, cur.rp, j + 1);
-                if (end - start <= a.seg_len)
-                    csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.first + j, -1);
-            }
-        } else if (STREAM == 1 && cur.long_idx < 0) {
+    auto process = [&](const CsrItem &cur, bool is_seg, int chunk) {
+        if (is_seg) {
+            // one piece of a cut row (partial sum + merge by the last arriver), or - tiny-split plans - a whole row
+            const int long_idx = cur.w.x, start = cur.w.y, end = cur.w.z;
+            if (long_idx < 0) csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, ~long_idx, -1);
+            else csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.w.w, long_idx);
+            return;
+        }
+        const int rp = cur.w.x;
+        if (STREAM == 1) {
             // rows longer than seg_len are covered by their segments: stream the row blocks between them
-            const int deg = __shfl_down_sync(FULL, cur.rp, 1) - cur.rp;
+            const int deg = __shfl_down_sync(FULL, rp, 1) - rp;
             const unsigned long_rows = __ballot_sync(FULL, lane < cur.count && deg > a.seg_len);
             int ja = 0;
             while (ja < cur.count) {
                 const unsigned rest = long_rows >> ja;
                 const int jb = rest ? ja + (__ffs(rest) - 1) : cur.count;
-                if (jb > ja) csr_stream_rows<T, E, G, 4, 2, UNIT>(a, cur.first, ja, jb, cur.rp, chunk);
+                if (jb > ja) csr_stream_rows<T, E, G, 4, 2, UNIT>(a, cur.first, ja, jb, rp, chunk);
                 ja = jb + 1;
             }
-        } else if (cur.long_idx >= 0) {
-            csr_process_range<T, E, G, NV, UNIT>(a, __shfl_sync(FULL, cur.rp, 0), __shfl_sync(FULL, cur.rp, 1), chunk,
-                                                 cur.first, cur.long_idx);
         } else {
+            // (STREAM == 2, the tiny-split family, has no row items: every row of its plans is a segment item)
             for (int j = 0; j < cur.count; ++j) {
-                const int start = __shfl_sync(FULL, cur.rp, j);
-                const int end = __shfl_sync(FULL, cur.rp, j + 1);
+                const int start = __shfl_sync(FULL, rp, j);
+                const int end = __shfl_sync(FULL, rp, j + 1);
                 if (end - start <= a.seg_len)      // longer rows are covered by their segments
                     csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.first + j, -1);
             }
@@ -760,7 +770,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
                 if (lane == 0) pend = atomicAdd(cnt, 1);         // for the item after next: not awaited here
                 nxt = csr_load_item<T>(a, sp, nit);
             }
-            process(cur, chunk);
+            process(cur, sp.x < 0, chunk);
             it = nit;
             cur = nxt;
         }

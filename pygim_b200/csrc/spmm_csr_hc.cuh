@@ -184,13 +184,12 @@ __global__ void __launch_bounds__(THREADS, 1) csr_hc_kernel(const __grid_constan
                 nxt = csr_load_item<T>(a, sp, nit);
                 if (sp.x >= 0) nxt_hot = __ldg(h.hot_cnt + min(nxt.first + lane, a.nrows - 1));
             }
-            if (cur.long_idx >= 0) {
-                csr_process_range<T, E, G, NV, UNIT>(a, __shfl_sync(FULL, cur.rp, 0), __shfl_sync(FULL, cur.rp, 1), chunk,
-                                                     cur.first, cur.long_idx);
+            if (sp.x < 0) {
+                csr_process_range<T, E, G, NV, UNIT>(a, cur.w.y, cur.w.z, chunk, cur.w.w, cur.w.x);
             } else {
                 for (int j = 0; j < cur.count; ++j) {
-                    const int start = __shfl_sync(FULL, cur.rp, j);
-                    const int end = __shfl_sync(FULL, cur.rp, j + 1);
+                    const int start = __shfl_sync(FULL, cur.w.x, j);
+                    const int end = __shfl_sync(FULL, cur.w.x, j + 1);
                     const int hot = __shfl_sync(FULL, cur_hot, j);
                     if (end - start > a.seg_len) continue;          // covered by its (cold) segments
                     Acc acc[E];

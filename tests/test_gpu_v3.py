@@ -26,6 +26,7 @@ def _want(oracle, adj, x):
     dict(item_nnz=32), dict(item_nnz=2048), dict(super_nnz=64), dict(super_nnz=1 << 20), dict(cta_threads=1024),
     dict(cta_threads=512, max_g=8), dict(max_g=4), dict(max_g=1), dict(rows_per_ticket=1), dict(seg_len=64, item_nnz=64),
     dict(short_rows=2, item_nnz=96), dict(short_rows=1), dict(short_rows=2, max_g=8, cta_threads=1024),
+    dict(short_rows=3), dict(short_rows=4), dict(short_rows=4, seg_len=64, max_g=2),
 ])
 def test_scheduling_options_do_not_change_results(gpu_backend, oracle, opts):
     from pygim_b200.backend_pim.spmm import prepare_pim_spmm
@@ -292,7 +293,9 @@ def test_spmv_batch_is_one_launch(gpu_backend, oracle):
     A = prepare_pim_spmv(adj, make_args(torch.int32, "COO", 64, 1, 32))
     out = A.mul(x)
     assert torch.equal(out, oracle_spmm(oracle, adj, x, torch.int32))
-    assert gpu_backend.last_launches(A.sp_info_ptr) == 1             # one 32-column launch per batch of vectors
+    # one 32-column batch per call, not one launch per vector (this degree-10 graph takes the two-launch family:
+    # tiny rows + the rest)
+    assert gpu_backend.last_launches(A.sp_info_ptr) <= 2
     # the op-level surface: `groups` single-column vectors
     pad = A.coo[0].size(1) - 203
     xb = torch.nn.functional.pad(x[:, :32], (0, 0, 0, pad))
@@ -320,3 +323,71 @@ def test_autotuned_pick_is_close_to_the_best_candidate(gpu_backend, oracle):
         times = autotuner.measure_options(A, x, cands, repeats=7)
         assert times[0] <= 1.10 * min(times), (shape, list(zip(cands, times)))
         A.free()
+
+
+def test_batched_host_pipeline_matches_the_oracle(gpu_backend, oracle):
+    """pygim_spmm_run_many_host: the hidden-size sweep as ONE upload / compute / download pipeline over pinned host
+    operands.  Big enough that the 128-byte column tiles and the row chunks of the last tile are exercised
+    (>= 8 MB results), CSR and sorted COO, float and integer; results equal the oracle element for element; a
+    second pass re-uses the staging buffers and the row-chunk plans."""
+    from pygim_b200.backend_pim.spmm import prepare_pim_spmm
+    adj = _reddit_like(scale=0.12, seed=5)
+    n = adj.size(0)
+    adj_d = adj.to("cuda")
+    cases = [(torch.float32, "CSR", 128), (torch.float32, "CSR", 16), (torch.int32, "COO", 96), (torch.float32, "CSR", 64),
+             (torch.int8, "CSR", 32), (torch.float32, "COO", 7)]
+    plans, xs, outs, wants = [], [], [], []
+    for dtype, fmt, hidden in cases:
+        x = features(n, hidden, dtype, seed=hidden)
+        wants.append(_want(oracle, adj, x))
+        plans.append(prepare_pim_spmm(adj_d, make_args(dtype, fmt, hidden)))
+        xs.append(x.pin_memory())
+        outs.append(torch.empty((n, hidden), dtype=dtype).pin_memory())
+    for _ in range(2):
+        for o in outs:
+            o.fill_(99)
+        gpu_backend.spmm_run_dense_many([p.sp_info_ptr for p in plans], xs, outs)
+        for (dtype, fmt, hidden), got, want in zip(cases, outs, wants):
+            assert torch.equal(got, want), (dtype, fmt, hidden)
+    # a strided (column-sliced) result and operand: the batch honours the row strides
+    wide_x = torch.zeros((n, 160), dtype=torch.float32).pin_memory()
+    wide_c = torch.full((n, 200), -1.0).pin_memory()
+    wide_x[:, 16:144] = xs[0]
+    gpu_backend.spmm_run_dense_many([plans[0].sp_info_ptr], [wide_x[:, 16:144]], [wide_c[:, 8:136]])
+    assert torch.equal(wide_c[:, 8:136], wants[0]) and bool((wide_c[:, :8] == -1).all()) and bool((wide_c[:, 136:] == -1).all())
+    # one plan twice in a batch is refused (its staging buffers are per plan), nothing is left in flight
+    with pytest.raises(Exception):
+        gpu_backend.spmm_run_dense_many([plans[1].sp_info_ptr, plans[1].sp_info_ptr], [xs[1], xs[1]], [outs[1], outs[1].clone()])
+    for p in plans:
+        p.free()
+
+
+@pytest.mark.parametrize("fmt", ["CSR", "COO"])
+def test_tiny_row_launch_on_a_citation_shaped_graph(gpu_backend, oracle, fmt):
+    """Graphs of mean degree < 12 take the two-launch family by default (short_rows = 4): rows of at most 8 nonzeros
+    by a matrix-wide grid of lane groups (csr_tiny_rows_kernel), the others - including segmented hubs - by the
+    persistent kernel.  Empty rows, rows of exactly 8 and 9 nonzeros, every dtype, explicit values, ragged widths,
+    accumulating sparse parts; bit-exact against the oracle."""
+    from pygim_b200 import graphgen
+    from pygim_b200.backend_pim.spmm import prepare_pim_spmm
+    adj = graphgen.synthetic_adj("arxiv", scale=0.2, seed=4)
+    n = adj.size(0)
+    rowptr, col, _ = adj.csr()
+    deg = rowptr[1:] - rowptr[:-1]
+    assert int((deg <= 8).sum()) > n // 2 and int(deg.max()) > 512 and bool((deg == 8).any()) and bool((deg == 9).any())
+    for dtype, hidden in ((torch.float32, 32), (torch.float32, 128), (torch.float32, 5), (torch.int8, 48), (torch.int16, 64),
+                          (torch.int32, 16), (torch.int64, 20), (torch.float64, 256)):
+        g = torch.Generator().manual_seed(hidden)
+        val = torch.randint(-3, 4, (col.numel(),), generator=g, dtype=torch.int32).to(dtype)
+        for value in (None, val):
+            a = type(adj)(rowptr=rowptr, col=col, value=value, sparse_sizes=(n, n), is_sorted=True)
+            x = features(n, hidden, dtype, seed=hidden + 1)
+            want = torch.from_numpy(oracle.spmm_csr_rowpar(rowptr.numpy(), col.numpy(), None if value is None else value.numpy(),
+                                                           x.numpy()))
+            for sp in (1, 2):
+                A = prepare_pim_spmm(a.to("cuda"), make_args(dtype, fmt, hidden, sp_parts=sp))
+                got = A.mul(x.cuda())
+                got = A.mul(x.cuda())
+                torch.cuda.synchronize()
+                assert torch.equal(got.cpu(), want), (dtype, hidden, fmt, value is not None, sp)
+                A.free()
