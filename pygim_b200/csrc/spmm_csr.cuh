@@ -653,12 +653,13 @@ __global__ void __launch_bounds__(256, (E >= 8) ? 4 : 8) csr_tiny_rows_kernel(co
 
 // ---------------------------------------------------------------------------------------------- scheduling
 struct CsrItem {
-    int first;         // rows: first row of the item (from the ticket by arithmetic)
-    int count;         // rows covered (1 for a segment)
     int4 w;            // LOADED, and not touched before the item is processed (so the load stays asynchronous):
                        //   rows:    w.x = this lane's rowptr entry, lane l holds rowptr[first + l] (l <= count)
                        //   segment: the Seg descriptor (long_idx, start, end, slot)
 };
+// rows of row item `it` of superticket `sp` (arithmetic only)
+__device__ __forceinline__ int csr_item_first(const int4 &sp, int it) { return sp.x + it * sp.z; }
+__device__ __forceinline__ int csr_item_count(const int4 &sp, int it) { return min(sp.z, sp.y - it * sp.z); }
 
 // Item `it` of superticket `sp`.  Its address follows from the ticket by arithmetic alone: ONE dependent load
 // (rowptr entries, or the segment descriptor as one 16-byte word) between drawing a ticket and having the item.
@@ -668,15 +669,8 @@ struct CsrItem {
 template <typename T> __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, const int4 &sp, int it) {
     CsrItem r;
     const int lane = threadIdx.x & 31;
-    if (sp.x < 0) {
-        r.first = 0;
-        r.count = 1;
-        r.w = __ldg(reinterpret_cast<const int4 *>(a.segs + (~sp.x + it)));
-    } else {
-        r.first = sp.x + it * sp.z;
-        r.count = min(sp.z, sp.x + sp.y - r.first);
-        r.w.x = a.rowptr[min(r.first + lane, a.nrows)];
-    }
+    if (sp.x < 0) r.w = __ldg(reinterpret_cast<const int4 *>(a.segs + (~sp.x + it)));
+    else r.w.x = a.rowptr[min(csr_item_first(sp, it) + lane, a.nrows)];
     return r;
 }
 
@@ -714,33 +708,34 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
     const int lane = threadIdx.x & 31;
     const int n_units = a.n_super * a.col_chunks;
 
-    auto process = [&](const CsrItem &cur, bool is_seg, int chunk) {
-        if (is_seg) {
+    auto process = [&](const CsrItem &cur, const int4 &sp, int it, int chunk) {
+        if (sp.x < 0) {
             // one piece of a cut row (partial sum + merge by the last arriver), or - tiny-split plans - a whole row
             const int long_idx = cur.w.x, start = cur.w.y, end = cur.w.z;
             if (long_idx < 0) csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, ~long_idx, -1);
             else csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.w.w, long_idx);
             return;
         }
+        const int first = csr_item_first(sp, it), count = csr_item_count(sp, it);
         const int rp = cur.w.x;
         if (STREAM == 1) {
             // rows longer than seg_len are covered by their segments: stream the row blocks between them
             const int deg = __shfl_down_sync(FULL, rp, 1) - rp;
-            const unsigned long_rows = __ballot_sync(FULL, lane < cur.count && deg > a.seg_len);
+            const unsigned long_rows = __ballot_sync(FULL, lane < count && deg > a.seg_len);
             int ja = 0;
-            while (ja < cur.count) {
+            while (ja < count) {
                 const unsigned rest = long_rows >> ja;
-                const int jb = rest ? ja + (__ffs(rest) - 1) : cur.count;
-                if (jb > ja) csr_stream_rows<T, E, G, 4, 2, UNIT>(a, cur.first, ja, jb, rp, chunk);
+                const int jb = rest ? ja + (__ffs(rest) - 1) : count;
+                if (jb > ja) csr_stream_rows<T, E, G, 4, 2, UNIT>(a, first, ja, jb, rp, chunk);
                 ja = jb + 1;
             }
         } else {
             // (STREAM == 2, the tiny-split family, has no row items: every row of its plans is a segment item)
-            for (int j = 0; j < cur.count; ++j) {
+            for (int j = 0; j < count; ++j) {
                 const int start = __shfl_sync(FULL, rp, j);
                 const int end = __shfl_sync(FULL, rp, j + 1);
                 if (end - start <= a.seg_len)      // longer rows are covered by their segments
-                    csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, cur.first + j, -1);
+                    csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, first + j, -1);
             }
         }
     };
@@ -770,7 +765,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
                 if (lane == 0) pend = atomicAdd(cnt, 1);         // for the item after next: not awaited here
                 nxt = csr_load_item<T>(a, sp, nit);
             }
-            process(cur, sp.x < 0, chunk);
+            process(cur, sp, it, chunk);
             it = nit;
             cur = nxt;
         }

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, 1) csr_hc_kernel(const __grid_constan
         int cur_hot = 0;
         if (it < sp.w) {
             cur = csr_load_item<T>(a, sp, it);
-            if (sp.x >= 0) cur_hot = __ldg(h.hot_cnt + min(cur.first + lane, a.nrows - 1));
+            if (sp.x >= 0) cur_hot = __ldg(h.hot_cnt + min(csr_item_first(sp, it) + lane, a.nrows - 1));
         }
         while (it < sp.w) {
             const int nit = take();
@@ -182,12 +182,13 @@ __global__ void __launch_bounds__(THREADS, 1) csr_hc_kernel(const __grid_constan
             int nxt_hot = 0;
             if (nit < sp.w) {
                 nxt = csr_load_item<T>(a, sp, nit);
-                if (sp.x >= 0) nxt_hot = __ldg(h.hot_cnt + min(nxt.first + lane, a.nrows - 1));
+                if (sp.x >= 0) nxt_hot = __ldg(h.hot_cnt + min(csr_item_first(sp, nit) + lane, a.nrows - 1));
             }
             if (sp.x < 0) {
                 csr_process_range<T, E, G, NV, UNIT>(a, cur.w.y, cur.w.z, chunk, cur.w.w, cur.w.x);
             } else {
-                for (int j = 0; j < cur.count; ++j) {
+                const int first = csr_item_first(sp, it), count = csr_item_count(sp, it);
+                for (int j = 0; j < count; ++j) {
                     const int start = __shfl_sync(FULL, cur.w.x, j);
                     const int end = __shfl_sync(FULL, cur.w.x, j + 1);
                     const int hot = __shfl_sync(FULL, cur_hot, j);
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1) csr_hc_kernel(const __grid_constan
                                                                                  start + hot, end, active);
 #pragma unroll
                     for (int k = 0; k < E; ++k) acc[k] += cold.v[k];
-                    csr_store_row<T, E, G>(a, acc, cur.first + j, vec, sub == 0 && active);
+                    csr_store_row<T, E, G>(a, acc, first + j, vec, sub == 0 && active);
                 }
             }
             it = nit;
