@@ -352,6 +352,35 @@ class SweepWorkload:
             ms, per_h = float(t[0]), [float(v) for v in t[1:]]
         return ms, per_h
 
+    def graph_us(self, reps=10, replays=5):
+        """Per-hidden device time (us) of one SpMM as a CUDA-graph replay of `reps` back-to-back calls: what a launch
+        costs without the host's enqueue path - the figure that matters for graphs whose SpMM takes tens of us."""
+        import torch
+        assert self.world == 1
+        out = []
+        cur = torch.cuda.current_stream()
+        for h in self.sweep:
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.ops[h].mul(self.x_dev[h], out=self.c_full[h])
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    self.ops[h].mul(self.x_dev[h], out=self.c_full[h])
+            g.replay()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(replays):
+                g.replay()
+            t1.record()
+            torch.cuda.synchronize()
+            out.append(t0.elapsed_time(t1) / (reps * replays) * 1e3)
+            del g
+        return out
+
     def flops_step(self):
         return sum(2.0 * self.nnz * h for h in self.sweep)
 
@@ -594,7 +623,7 @@ def run_ours(a):
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
                "mode": (a.e2e_mode if world == 1 else "row block of B per rank over PCIe + NVLink all-gather, "
                         "local rows of C back (bytes are totals over ranks)")}
-        if world == 1 and a.e2e_mode != "pipelined":
+        if world == 1:   # per call: exposed upload, kernel window, exposed download tail (pygim_last_timers)
             e2e["phases_ms"] = {str(h): pim_ops.last_timers(w.plans[h].sp_info_ptr) for h in sweep}
     clocks = sampler.stop() if rank == 0 else None
 
@@ -630,12 +659,14 @@ def run_ours(a):
         w.free()
 
     # ---- sub-records (same process, same box): the clustered graph with prepare-time reordering, products-shape
-    clustered_rec = products_rec = None
+    clustered_rec = products_rec = arxiv_rec = None
     if a.shape == "reddit" and not a.clustered and a.dtype == "FLT32" and a.format == "CSR" and not a.hidden:
         if world == 1 and not a.no_clustered:
             clustered_rec = run_sub_workload(a, "reddit", dev, rank, world, peak, clustered=True)
         if not a.no_products:
             products_rec = run_sub_workload(a, "products", dev, rank, world, peak, clustered=False)
+        if world == 1 and not a.no_arxiv:
+            arxiv_rec = run_small_graph(a, "arxiv", dev, peak)
 
     if rank != 0:
         if world > 1:
@@ -739,12 +770,42 @@ def run_ours(a):
         "roofline": roof, "per_hidden": per_hidden, "cpu_baseline": cpu, "clocks": clocks,
         "parity_all_ranks": parity, "parity_rows_checked_per_rank": parity_rows, "parity_e2e": parity_e2e,
         "no_exchange": no_exchange, "selftest_multi": None if selftest is None else {"ok": selftest[0], "modes": selftest[1]},
-        "clustered": clustered_rec, "products": products_rec, "reorder_stats": w.reorder_stats,
+        "clustered": clustered_rec, "products": products_rec, "arxiv": arxiv_rec, "reorder_stats": w.reorder_stats,
         "lib": os.path.relpath(__import__("pygim_b200._lib", fromlist=["x"]).loaded_path() or "", ROOT),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_small_graph(a, shape, dev, peak):
+    """arxiv-shape (BASELINE.json configs[0], the reference's own CPU-runnable case): an SpMM takes tens of
+    microseconds, so it is timed both call by call (CUDA events, host enqueue included) and as a CUDA-graph replay,
+    and EVERY element is compared with the oracle."""
+    import torch
+    from oracle import oracle as O
+    w = SweepWorkload(a, shape, dev, 0, 1)
+    ms, per_h = w.timed(max(5, min(a.steps, 10)), 3)
+    us = w.graph_us()
+    rec = {"config": {"workload": "%s-shape FLT32 CSR SpMM, hidden sweep %s" % (shape, "/".join(map(str, w.sweep))),
+                      "nodes": w.n, "edges": w.nnz},
+           "value": w.flops_step() / (sum(us) * 1e-6) / 1e9, "unit": UNIT, "timing": "CUDA-graph replay",
+           "per_hidden": [{"hidden": h, "graph_us": u, "per_call_events_us": p * 1e3, "gflops": 2.0 * w.nnz * h / (u * 1e-6) / 1e9,
+                           "frac_hbm": alg_bytes_csr(w.n, w.n, w.nnz, h, w.esize, a.format) / (u * 1e-6) / 1e9 / peak}
+                          for h, u, p in zip(w.sweep, us, per_h)]}
+    if not a.no_check:
+        O.build()
+        rp, cl, _ = w.adj_plain.csr()
+        rp, cl = rp.cpu().numpy().astype("int32"), cl.cpu().numpy().astype("int32")
+        bad = 0
+        for h in w.sweep:
+            got = w.ops[h].mul(w.x_dev[h], out=w.c_full[h])
+            torch.cuda.synchronize()
+            want = O.spmm_csr_rowpar(rp, cl, None, w.x_dev[h].cpu().numpy(), nthreads=O.max_threads())
+            bad += int((got.cpu().numpy() != want).sum())
+        rec["parity_whole_matrix"] = bad == 0
+    w.free()
+    return rec
 
 
 def run_sub_workload(a, shape, dev, rank, world, peak, clustered):
@@ -922,6 +983,7 @@ def main():
     ap.add_argument("--no-selftest", action="store_true", help="N > 1: skip the whole-matrix multi-GPU self-test")
     ap.add_argument("--no-clustered", action="store_true", help="skip the clustered-graph sub-record (N = 1)")
     ap.add_argument("--no-products", action="store_true", help="skip the products-shape sub-record")
+    ap.add_argument("--no-arxiv", action="store_true", help="skip the arxiv-shape sub-record (N = 1)")
     ap.add_argument("--workload", default="spmm", choices=["spmm", "inference"],
                     help="spmm = the headline hidden sweep; inference = 2-layer GCN/GIN/SAGE end to end (configs[3])")
     a = ap.parse_args()

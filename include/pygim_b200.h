@@ -117,13 +117,18 @@ PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle);
  *   max_g            lanes per dense row are capped at this power of two; wider rows run as column chunks of one
  *                    launch (8 = 128-byte chunks, the L1 line)
  *   short_rows       CSR kernel family: 0 deep (128 registers, 16 gathers per lane in flight), 1 high occupancy
- *                    (40 registers), 2 streamed row items, 3 light (64 registers, 8 gathers), 4 one lane group per
- *                    row; automatic: 4 when the mean degree is below 12, 3 below 96, else 0
+ *                    (40 registers), 2 streamed row items, 3 light (64 registers, 8 gathers), 4 two launches - rows of
+ *                    at most 8 nonzeros by a matrix-wide grid of lane groups, the rest as <= seg_len pieces, longest
+ *                    first; automatic: 4 when the mean degree is below 12, 3 below 96, else 0.  The family shapes
+ *                    the plan: setting it re-plans
  *   unit_values      0 forces the general kernels even when every stored value is one
  *   coo_native       1 runs a sorted COO plan through the COO (segmented reduction) kernel instead of the CSR
  *                    kernels over the derived row pointer
  *   chunk_nnz        COO kernel: nonzeros per work item
  *   host_chunks      row chunks of the host entry point (0 = no download/compute overlap)
+ *   host_tile_bytes  bytes per dense row of one upload / compute / download column tile of the host entry points
+ *                    (multiple of 128; default 256: narrower 2-D PCIe copies lose a third of the rate when both
+ *                    directions are busy)
  *   l2_persist       1/0 forces / forbids the access-policy window (persisting L2 lines) over the dense tile of a
  *                    launch; automatic = on when the tile fits the carve-out */
 PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int64_t value);
@@ -163,7 +168,7 @@ PYGIM_API int pygim_spmm_run_group_device(pygim_handle_t handle, int n_ds, const
 /* A BATCH of host-operand SpMMs - the hidden-size sweep of spmm_test.py:119-132 (one prepare + mul per dense size),
  * or the layers of inference.py:142-149 - as ONE software pipeline: call k runs handles[k] on the host matrix B[k]
  * ([sum ncols x h_size_k], row stride ldb[k] elements) into the host matrix C[k] (row stride ldc[k]).  All uploads
- * share one stream and run in the order given, tile by tile (128-byte column tiles); the kernels of a tile start as
+ * share one stream and run in the order given, tile by tile (256-byte column tiles); the kernels of a tile start as
  * soon as it has landed; every finished tile downloads while the next computes.  Per-call entry points expose the
  * first upload and the last download of EVERY call; the batch exposes one tile's upload and a quarter of one tile's
  * download in total.  Order the calls by ascending operand size so the kernels start early.  A plan may appear once

@@ -172,6 +172,7 @@ struct Group {
     long long opt_unit_values = -1;   // 0 forces the general (weighted) kernels
     long long opt_short_rows = -1;    // 1/0 force the high-occupancy / deep-unroll CSR instantiation
     long long opt_host_chunks = -1;   // host entry point: row chunks for download/compute overlap (0 = off)
+    long long opt_host_tile_bytes = -1;   // host entry point: bytes per row of one upload/compute column tile (default 256)
     long long opt_coo_native = -1;    // 1: sorted COO streams also run through the COO kernel
     int *d_row_map = nullptr;         // plan row r -> result row (row reordering); null = identity
     std::mutex mu;                    // guards `scratch`
@@ -950,6 +951,9 @@ PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int6
         g->opt_short_rows = value;
     } else if (!std::strcmp(key, "host_chunks")) {
         g->opt_host_chunks = value;
+    } else if (!std::strcmp(key, "host_tile_bytes")) {
+        if (value > 0 && value % 128) return fail(PYGIM_ERR_INVALID, "host_tile_bytes must be a multiple of 128");
+        g->opt_host_tile_bytes = value;
     } else if (!std::strcmp(key, "coo_native")) {
         if (g->format != PYGIM_COO) return fail(PYGIM_ERR_INVALID, "coo_native applies to COO plans");
         g->opt_coo_native = value;
@@ -1161,25 +1165,42 @@ static int host_enqueue(Group *g, int n_ds, const void *const *B_parts, const in
     const bool pipelined = g->opt_host_chunks != 0 &&
                            (g->opt_host_chunks > 0 || rowsC * H * s >= (size_t)(8u << 20));
 
-    // ---- column tiles
+    // ---- column tiles.  Measured on the B200 box (tools/pcie_probe.py, profiles/r02_pcie_probe.txt): 2-D copies of
+    // >= 256-byte row pieces run at the full PCIe rate (55 GB/s alone, 50 GB/s per direction with both busy); 128-byte
+    // pieces reach 51 / 47 GB/s alone but only 35 GB/s per direction when uploads and downloads overlap - and in a
+    // pipeline they always do (sweep step: 7.85 ms with 128-byte tiles, 7.47 ms with 256-byte tiles; thin tiles only
+    // at the ends of the batch: 8.1 ms).  So tiles are 256 bytes wide (64 FLT32 columns: also the widest tile whose
+    // gathers stay L2-resident on Reddit-shape); a remainder is one 128-byte tile.
     struct Tile { int part; size_t col0, width, dev_off; const char *host; size_t host_ld; };
     std::vector<Tile> tiles;
     size_t col = 0, dev_off = 0;
+    const size_t wide = g->opt_host_tile_bytes > 0 ? (size_t)g->opt_host_tile_bytes : 256;
+    const size_t thin = std::min<size_t>(wide, 128);
     for (int j = 0; j < n_ds; ++j) {
         const size_t w = (size_t)g->dense_cols[j];
-        size_t n_t = 1;
-        if (pipelined && w * s >= 256 && (w * s) % 128 == 0) n_t = w * s / 128;
-        const size_t tw = w / n_t;
-        for (size_t t = 0; t < n_t; ++t) {
+        std::vector<size_t> widths;     // in bytes
+        if (pipelined && w * s >= 2 * thin && (w * s) % thin == 0) {
+            size_t left = w * s;
+            while (left > 0) {
+                const size_t t = std::min(left, (left % wide) ? thin : wide);
+                widths.push_back(t);
+                left -= t;
+            }
+        } else {
+            widths.push_back(w * s);
+        }
+        size_t off = 0;
+        for (size_t t = 0; t < widths.size(); ++t) {
             Tile tl;
             tl.part = j;
-            tl.col0 = col + t * tw;
-            tl.width = tw;
+            tl.col0 = col + off / s;
+            tl.width = widths[t] / s;
             tl.dev_off = dev_off;
-            tl.host = static_cast<const char *>(B_parts[j]) + t * tw * s;
+            tl.host = static_cast<const char *>(B_parts[j]) + off;
             tl.host_ld = (size_t)ldb[j];
-            if (tw) tiles.push_back(tl);
-            dev_off += rowsB * tw * s;
+            if (tl.width) tiles.push_back(tl);
+            dev_off += rowsB * widths[t];
+            off += widths[t];
         }
         col += w;
     }

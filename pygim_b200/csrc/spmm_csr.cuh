@@ -666,10 +666,13 @@ __device__ __forceinline__ int csr_item_count(const int4 &sp, int it) { return m
 // Nothing here consumes the loaded registers: any arithmetic on them would make the warp wait for the load right
 // here instead of after the previous item's work (measured on arxiv-shape: two overlapping scalar loads into one
 // register cost a full memory latency per item, 29 % of all stall samples).
-template <typename T> __device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, const int4 &sp, int it) {
+// SEGS_ONLY (tiny-split plans: no row items): the row-pointer load is compiled out - predicated off it would still
+// wait on the descriptor load's scoreboard (same destination register), 15 % of that kernel's stall samples.
+template <typename T, bool SEGS_ONLY = false>
+__device__ __forceinline__ CsrItem csr_load_item(const CsrArgs<T> &a, const int4 &sp, int it) {
     CsrItem r;
     const int lane = threadIdx.x & 31;
-    if (sp.x < 0) r.w = __ldg(reinterpret_cast<const int4 *>(a.segs + (~sp.x + it)));
+    if (SEGS_ONLY || sp.x < 0) r.w = __ldg(reinterpret_cast<const int4 *>(a.segs + (~sp.x + it)));
     else r.w.x = a.rowptr[min(csr_item_first(sp, it) + lane, a.nrows)];
     return r;
 }
@@ -709,7 +712,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
     const int n_units = a.n_super * a.col_chunks;
 
     auto process = [&](const CsrItem &cur, const int4 &sp, int it, int chunk) {
-        if (sp.x < 0) {
+        if (STREAM == 2 || sp.x < 0) {
             // one piece of a cut row (partial sum + merge by the last arriver), or - tiny-split plans - a whole row
             const int long_idx = cur.w.x, start = cur.w.y, end = cur.w.z;
             if (long_idx < 0) csr_process_range<T, E, G, NV, UNIT>(a, start, end, chunk, ~long_idx, -1);
@@ -756,14 +759,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             pend = atomicAdd(cnt, 1);
         }
         CsrItem cur;
-        if (it < n) cur = csr_load_item<T>(a, sp, it);
+        if (it < n) cur = csr_load_item<T, STREAM == 2>(a, sp, it);
         while (it < n) {
             const int nit = __shfl_sync(FULL, pend, 0);          // drawn one item ago
             if (lane == 0 && nit == n) atomicAdd(a.warps_out + 1, 1u);
             CsrItem nxt;
             if (nit < n) {
                 if (lane == 0) pend = atomicAdd(cnt, 1);         // for the item after next: not awaited here
-                nxt = csr_load_item<T>(a, sp, nit);
+                nxt = csr_load_item<T, STREAM == 2>(a, sp, nit);
             }
             process(cur, sp, it, chunk);
             it = nit;

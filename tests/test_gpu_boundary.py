@@ -149,8 +149,9 @@ def test_cuda_graph_capture_and_replay(gpu_backend, oracle, fmt):
 
 @pytest.mark.parametrize("fmt", ["CSR", "COO"])
 def test_pipelined_host_entry_point(gpu_backend, oracle, fmt):
-    """Host operands with the upload/compute/download pipeline forced on (column tiles of 128 bytes + row chunks
-    of the last tile), with several sparse and dense parts, 16-byte aligned and unaligned widths."""
+    """Host operands with the upload/compute/download pipeline forced on (column tiles of 256 bytes by default, 128 /
+    512 by option, a 128-byte remainder tile + row chunks of the last tile), with several sparse and dense parts,
+    16-byte aligned and unaligned widths."""
     from pygim_b200.backend_pim import pim_ops
     from pygim_b200.backend_pim.spmm import prepare_pim_spmm
     for dtype, hidden, sp, ds in ((torch.float32, 128, 1, 1), (torch.float32, 96, 2, 2), (torch.int8, 256, 1, 1),
@@ -159,10 +160,11 @@ def test_pipelined_host_entry_point(gpu_backend, oracle, fmt):
         x = features(700, hidden, dtype, seed=2)
         want = oracle_spmm(oracle, adj, x, dtype)
         A = prepare_pim_spmm(adj, make_args(dtype, fmt, hidden, sp_parts=sp, ds_parts=ds))
-        for chunks in (3, 1, 0):
+        for chunks, tile in ((3, 128), (3, -1), (1, 512), (0, -1)):
             pim_ops.plan_set_option(A.sp_info_ptr, "host_chunks", chunks)
+            pim_ops.plan_set_option(A.sp_info_ptr, "host_tile_bytes", tile)
             out = torch.empty((700, hidden), dtype=dtype).pin_memory()
             got = A.mul(x.pin_memory(), out=out)
-            assert torch.equal(got, want), (dtype, hidden, sp, ds, chunks)
-            assert torch.equal(A.mul(x), want), (dtype, hidden, sp, ds, chunks, "pageable")
+            assert torch.equal(got, want), (dtype, hidden, sp, ds, chunks, tile)
+            assert torch.equal(A.mul(x), want), (dtype, hidden, sp, ds, chunks, tile, "pageable")
         A.free()
