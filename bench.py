@@ -152,6 +152,17 @@ def cpu_sample_graph(n, nnz, max_deg, sample_rows, seed=0):
     return rowptr.numpy().astype("int32"), col.numpy().astype("int32")
 
 
+def workload_config(shape, clustered, dtype, fmt, sweep, n, nnz):
+    """The `config` block: what is computed, identically worded in both arms (`--impl ours` / `--impl reference`).
+    How OUR arm executes it (column tiling, sharding, fast paths) is the separate `plan` block."""
+    return {"workload": "%s-shape%s %s %s SpMM, hidden sweep %s" % (shape, " (block-model communities)" if clustered else "",
+                                                                    dtype, fmt, "/".join(map(str, sweep))),
+            "nodes": n, "edges": nnz, "hidden_sweep": list(sweep), "format": fmt, "sp_parts": 1,
+            "values": "all ones (value-less adjacency)", "features": "integers in [-8, 3] (spmm_test.py:70)",
+            "l2": "inputs larger than L2 (A = %.0f MB is streamed every launch; nothing is cached between steps)"
+                  % ((8.0 * nnz) / 1e6)}
+
+
 def run_reference(a):
     """--impl reference: PyGim's CPU path timed on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -184,8 +195,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / max(a.steps, 1) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "reddit-shape FLT32 CSR SpMM, hidden sweep 16/32/64/128", "nodes": n, "edges": nnz,
-                   "hidden_sweep": HIDDEN_SWEEP, "format": "CSR"},
+        "config": workload_config(SHAPE, False, "FLT32", "CSR", HIDDEN_SWEEP, n, nnz),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "native_build": bool(native)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -751,21 +761,18 @@ def run_ours(a):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"FLT32": "f32", "DBL64": "f64", "INT8": "i8", "INT16": "i16", "INT32": "i32", "INT64": "i64"}[a.dtype],
         "data": "synthetic",
-        "config": {"workload": "%s-shape%s %s %s SpMM, hidden sweep %s" % (a.shape, " (block-model communities)" if a.clustered else "",
-                                                                            a.dtype, a.format, "/".join(map(str, sweep))),
-                   "nodes": n, "edges": nnz, "hidden_sweep": sweep, "format": a.format, "sp_parts": 1,
-                   "values": "all ones (value-less adjacency); " + ("general weighted kernel forced" if a.general_kernel
-                             else "unit-value fast path: value stream not read, results bit-identical"),
-                   "ds_parts": {str(h): ds_parts[h] for h in sweep},
-                   "reorder": a.reorder or "none",
-                   "sharding": ("rows by nnz over %d GPUs, B replicated, all-gather of C %s, inside the timing"
-                                % (world, ("fused into the kernel epilogue (NVLink %s stores, %s)"
-                                           % ("per-peer" if a.no_multicast else "multimem",
-                                              "in-kernel arrival flags, no barrier" if a.sync == "flags" else "one barrier per call"))
-                                   if w.gather == "fused" else "by NCCL"))
-                   if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2 (A = %.0f MB streams through a %.0f MB L2 every launch)"
-                         % ((8.0 * nnz) / 1e6, w.info["l2_bytes"] / 1e6)},
+        "config": workload_config(a.shape, a.clustered, a.dtype, a.format, sweep, n, nnz),
+        "plan": {"values": ("general weighted kernel forced" if a.general_kernel
+                            else "unit-value fast path: value stream not read, results bit-identical"),
+                 "ds_parts": {str(h): ds_parts[h] for h in sweep},
+                 "reorder": a.reorder or "none",
+                 "sharding": ("rows by nnz over %d GPUs, B replicated, all-gather of C %s, inside the timing"
+                              % (world, ("fused into the kernel epilogue (NVLink %s stores, %s)"
+                                         % ("per-peer" if a.no_multicast else "multimem",
+                                            "in-kernel arrival flags, no barrier" if a.sync == "flags" else "one barrier per call"))
+                                 if w.gather == "fused" else "by NCCL"))
+                 if world > 1 else "single GPU",
+                 "l2_bytes": w.info["l2_bytes"]},
         "e2e": e2e, "gpu_launches": launches_per_step * steps,
         "roofline": roof, "per_hidden": per_hidden, "cpu_baseline": cpu, "clocks": clocks,
         "parity_all_ranks": parity, "parity_rows_checked_per_rank": parity_rows, "parity_e2e": parity_e2e,

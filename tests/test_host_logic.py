@@ -169,3 +169,5 @@ def test_bench_reference_arm_and_byte_model(tmp_path):
     assert line["impl"] == "reference" and line["unit"] == "GFLOP/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    # both arms describe the workload with the same `config` block (the driver compares them)
+    assert line["config"] == bench.workload_config("reddit", False, "FLT32", "CSR", [16, 32, 64, 128], n, nnz)
