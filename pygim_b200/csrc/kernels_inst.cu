@@ -123,7 +123,10 @@ static cudaError_t launch_csr_g(const CsrArgs<T> &a, const CsrLaunch &l, int64_t
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return e;
         }
-        return launch_csr_t<E, G, UNIT, CsrTuneLight<E, UNIT>, 2>(a, l, launches);
+        // the pieces run on the DEEP register budget (16 warps per SM, 16 gathers in flight): measured on arxiv-shape,
+        // H = 16 / 32 / 64 / 128, whole SpMM as a CUDA-graph replay - deep 32 / 37 / 54 / 104 us, light (32 warps) 39 / 43 /
+        // 59 / 120 us, high occupancy (48 warps) 46 / 55 / 73 / 120 us: fewer warps on the one ticket counter, deeper rounds
+        return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>, 2>(a, l, launches);
     }
     return launch_csr_t<E, G, UNIT, CsrTune<E, UNIT>>(a, l, launches);
 }

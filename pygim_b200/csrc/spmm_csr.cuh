@@ -746,17 +746,27 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
     // drain one (superticket, chunk): one atomic per item.  The atomic of item k+2 is ISSUED while item k+1's
     // rowptr / descriptor load is issued and item k is processed; its result is only read an item later, so neither
     // the L2 atomic nor the dependent load is on the critical path.
-    auto drain = [&](int unit) {
+    auto drain = [&](int unit, bool static_first) {
         const int s = unit / a.col_chunks, chunk = unit - s * a.col_chunks;
         const int4 sp = __ldg(a.supers + s);
         const int n = sp.w;
         int *cnt = a.super_cnt + unit;
         int pend = 0;                                   // lane 0: a ticket whose atomic may still be in flight
-        if (lane == 0) pend = atomicAdd(cnt, 1);
-        int it = __shfl_sync(FULL, pend, 0);
-        if (lane == 0) {
-            if (it == n) atomicAdd(a.warps_out + 1, 1u);          // exactly one warp draws ticket n: the unit is drawn out
-            pend = atomicAdd(cnt, 1);
+        int it;
+        // `static_first` (the unit EVERY warp of the launch drains first): warp w starts on item w without asking -
+        // otherwise the launch begins with n_warps atomics on one address, a few microseconds before the last warp
+        // has its first item - and the counter hands out the tickets from n_warps on.
+        const int base = static_first ? (int)a.n_warps : 0;
+        if (static_first) {
+            it = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+            if (lane == 0) pend = atomicAdd(cnt, 1) + base;
+        } else {
+            if (lane == 0) pend = atomicAdd(cnt, 1);
+            it = __shfl_sync(FULL, pend, 0);
+            if (lane == 0) {
+                if (it == n) atomicAdd(a.warps_out + 1, 1u);      // exactly one warp draws ticket n: the unit is drawn out
+                pend = atomicAdd(cnt, 1);
+            }
         }
         CsrItem cur;
         if (it < n) cur = csr_load_item<T, STREAM == 2>(a, sp, it);
@@ -765,7 +775,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             if (lane == 0 && nit == n) atomicAdd(a.warps_out + 1, 1u);
             CsrItem nxt;
             if (nit < n) {
-                if (lane == 0) pend = atomicAdd(cnt, 1);         // for the item after next: not awaited here
+                if (lane == 0) pend = atomicAdd(cnt, 1) + base;  // for the item after next: not awaited here
                 nxt = csr_load_item<T, STREAM == 2>(a, sp, nit);
             }
             process(cur, sp, it, chunk);
@@ -795,7 +805,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
         int unit;
         if (one_queue) {
             if (home_k >= n_units) break;
-            drain(home_k++);
+            drain(home_k, home_k == 0);
+            ++home_k;
             continue;
         }
         {   // one lane reads the shared progress (lanes need not be converged here), all lanes take its value
@@ -830,7 +841,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) csr_spmm_kernel(const __g
             scan_m &= scan_m - 1;
             unit = __shfl_sync(FULL, scan_u, src);
         }
-        drain(unit);
+        drain(unit, false);
         if (is_home) {          // drain returns only when the unit is drawn out: the block's other warps can skip it
             if (lane == 0) atomicMax(&s_home_done, home_k + 1);
             ++home_k;
