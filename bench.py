@@ -118,10 +118,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def auto_ds_parts(n_cols, hidden, info, s=4):
+def auto_ds_parts(n_cols, hidden, info, s=4, nnz=None):
     """Column tiling so that one B tile stays L2-resident next to the streaming A: see pygim_b200.utils.autotuner."""
     from pygim_b200.utils import autotuner
-    return autotuner.choose_ds_parts(n_cols, hidden, s, info["l2_bytes"])
+    return autotuner.choose_ds_parts(n_cols, hidden, s, info["l2_bytes"], nnz=nnz)
 
 
 def make_args(hidden, dtype, fmt="CSR"):
@@ -257,7 +257,7 @@ class SweepWorkload:
             del groups
             torch.cuda.synchronize()
             self.reorder_stats["seconds"] = time.perf_counter() - t0
-        self.ds_parts = {h: (a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, self.info, self.esize))
+        self.ds_parts = {h: (a.ds_parts if a.ds_parts > 0 else auto_ds_parts(n, h, self.info, self.esize, nnz=nnz))
                          for h in self.sweep}
         base = SparseTensorCOO(adj, dtype=self.dtype, format=a.format)
         base.row_perm = perm

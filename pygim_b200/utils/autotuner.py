@@ -97,10 +97,16 @@ class GraphStats:
                    int(deg.max()) if n else 0, std / mean if mean > 0 else 0.0, int((deg == 0).sum()))
 
 
-def choose_ds_parts(n_cols: int, hidden: int, elem_size: int, l2_bytes: int, l2_fraction: float = 0.46) -> int:
+def choose_ds_parts(n_cols: int, hidden: int, elem_size: int, l2_bytes: int, l2_fraction: float = 0.46,
+                    nnz: Optional[int] = None) -> int:
     """Smallest number (1, 2 or 4) of equal column tiles for which one B tile (n_cols x hidden/ds x elem_size)
     fits in `l2_fraction` of L2.  B200's L2 is two die-local halves and read-shared data ends up in both, so the
-    budget for the resident tile is well below the nominal 126 MB; the streaming A/C traffic needs room too."""
+    budget for the resident tile is well below the nominal 126 MB; the streaming A/C traffic needs room too.
+    Tiling buys L2 hits for rows that are gathered MANY times; when a feature row is gathered only a few times per
+    launch (`nnz` / `n_cols` < 32: citation-shaped graphs) there is nothing to keep resident and every extra tile
+    only repeats the launches (arxiv-shape H = 128: 136 us as two tiles, 105 us as one)."""
+    if nnz is not None and nnz < 32 * max(n_cols, 1):
+        return 1
     budget = l2_bytes * l2_fraction
     for ds in (1, 2, 4):
         if hidden % ds:
@@ -317,7 +323,7 @@ def tune_plan(adj, hidden_size: int, dtype=None, fmt: str = "CSR", cache_dir: Op
         except Exception:
             pass
         dev = DeviceModel.from_environment(info)
-    ds = choose_ds_parts(stats.ncols, hidden_size, elem, dev.l2_bytes, dev.l2_resident_fraction)
+    ds = choose_ds_parts(stats.ncols, hidden_size, elem, dev.l2_bytes, dev.l2_resident_fraction, nnz=stats.nnz)
     choice = {"sp_parts": 1, "ds_parts": ds, "options": kernel_options(stats, hidden_size, elem, reordered),
               "predicted_ms": predict_ms(stats, hidden_size, elem, 1, ds, dev, fmt), "source": "model"}
     cache[key] = {k: v for k, v in choice.items() if k != "source"}
