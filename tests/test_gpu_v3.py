@@ -391,3 +391,31 @@ def test_tiny_row_launch_on_a_citation_shaped_graph(gpu_backend, oracle, fmt):
                 torch.cuda.synchronize()
                 assert torch.equal(got.cpu(), want), (dtype, hidden, fmt, value is not None, sp)
                 A.free()
+
+
+def test_tiny_row_family_with_a_row_map_and_options(gpu_backend, oracle):
+    """The two-launch family under a row permutation (SM-affine piece supertickets with stealing, both launches
+    scatter through the row map), under explicit seg_len / super_nnz / cta_threads options, forced onto a graph that
+    would not choose it, and switched off again on one plan; results in the original row order, bit-exact."""
+    from pygim_b200 import graphgen
+    from pygim_b200.backend_pim.spmm import prepare_pim_spmm
+    for shape, scale in (("arxiv", 0.2), ("products", 0.01)):
+        adj = graphgen.synthetic_adj(shape, scale=scale, seed=9)
+        n = adj.size(0)
+        for dtype, hidden in ((torch.float32, 64), (torch.int16, 24)):
+            x = features(n, hidden, dtype, seed=5)
+            want = _want(oracle, adj, x)
+            for reorder in (None, "degree", "cluster"):
+                args = make_args(dtype, "CSR", hidden)
+                if reorder:
+                    args.reorder = reorder
+                A = prepare_pim_spmm(adj.to("cuda"), args)
+                for opts in (dict(short_rows=4), dict(short_rows=4, seg_len=32, super_nnz=4096), dict(short_rows=4, cta_threads=512),
+                             dict(short_rows=3), dict(short_rows=4)):
+                    for k, v in opts.items():
+                        gpu_backend.plan_set_option(A.sp_info_ptr, k, v)
+                    got = A.mul(x.cuda())
+                    got = A.mul(x.cuda())
+                    torch.cuda.synchronize()
+                    assert torch.equal(got.cpu(), want), (shape, dtype, hidden, reorder, opts)
+                A.free()
