@@ -669,7 +669,7 @@ def run_ours(a):
         w.free()
 
     # ---- sub-records (same process, same box): the clustered graph with prepare-time reordering, products-shape
-    clustered_rec = products_rec = arxiv_rec = None
+    clustered_rec = products_rec = arxiv_rec = column_rec = None
     if a.shape == "reddit" and not a.clustered and a.dtype == "FLT32" and a.format == "CSR" and not a.hidden:
         if world == 1 and not a.no_clustered:
             clustered_rec = run_sub_workload(a, "reddit", dev, rank, world, peak, clustered=True)
@@ -677,6 +677,8 @@ def run_ours(a):
             products_rec = run_sub_workload(a, "products", dev, rank, world, peak, clustered=False)
         if world == 1 and not a.no_arxiv:
             arxiv_rec = run_small_graph(a, "arxiv", dev, peak)
+        if world > 1 and not a.no_column_sharded:
+            column_rec = run_column_sharded(a, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -777,12 +779,67 @@ def run_ours(a):
         "roofline": roof, "per_hidden": per_hidden, "cpu_baseline": cpu, "clocks": clocks,
         "parity_all_ranks": parity, "parity_rows_checked_per_rank": parity_rows, "parity_e2e": parity_e2e,
         "no_exchange": no_exchange, "selftest_multi": None if selftest is None else {"ok": selftest[0], "modes": selftest[1]},
-        "clustered": clustered_rec, "products": products_rec, "arxiv": arxiv_rec, "reorder_stats": w.reorder_stats,
+        "clustered": clustered_rec, "products": products_rec, "arxiv": arxiv_rec, "column_sharded": column_rec,
+        "reorder_stats": w.reorder_stats,
         "lib": os.path.relpath(__import__("pygim_b200._lib", fromlist=["x"]).loaded_path() or "", ROOT),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_column_sharded(a, dev, rank, world):
+    """SURVEY.md 8(e) / north_star "optionally column-sharded": the FEATURE COLUMNS dealt over the GPUs (every rank
+    streams all of A and computes all rows of its H / N columns), with and without the all-gather of the column
+    blocks, for the wide end of the sweep - beside the row-sharded default of the main line."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from pygim_b200 import graphgen
+    from pygim_b200.backend_pim.spmm import TORCH_TYPES
+    from pygim_b200.sharded import ColumnShardedSpMM
+    from pygim_b200.sparse_tensor import SparseTensor
+    n, nnz, max_deg = graphgen.SHAPES["reddit"]
+    rowptr, col = graphgen.synthetic_csr(n, nnz, max_deg, seed=0, device=str(dev))
+    adj = SparseTensor(rowptr=rowptr, col=col, value=None, sparse_sizes=(n, n), is_sorted=True)
+    dtype = TORCH_TYPES[a.dtype]
+    rec = {"per_hidden": []}
+    ok = True
+    for h in (64, 128):
+        op = ColumnShardedSpMM(adj, make_args(h, dtype, a.format))
+        x = graphgen.reference_features(n, h, dtype, seed=h, device=str(dev))
+        times = {}
+        for gather in (True, False):
+            for _ in range(3):
+                out = op.mul(x, gather=gather)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(10):
+                out = op.mul(x, gather=gather)
+            t1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([t0.elapsed_time(t1) / 10], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times[gather] = float(t)
+        if not a.no_check:      # this rank's column block, first 512 rows, against the oracle
+            O.build()
+            rp = rowptr[:513].cpu().numpy().astype("int32")
+            cl = col[: int(rp[-1])].cpu().numpy().astype("int32")
+            want = O.spmm_csr_rowpar(rp, cl, None, x.cpu().numpy())
+            ok = ok and bool(np.array_equal(out[:512].cpu().numpy(), want[:, op.c0:op.c1]))
+        rec["per_hidden"].append({"hidden": h, "columns_per_gpu": op.c1 - op.c0, "ms_with_all_gather": times[True],
+                                  "ms_without": times[False], "gflops_with_all_gather": 2.0 * nnz * h / times[True] / 1e6,
+                                  "gflops_without": 2.0 * nnz * h / times[False] / 1e6})
+        op.free()
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    rec["parity_all_ranks"] = bool(float(flag) == 1.0) if not a.no_check else None
+    del adj, rowptr, col
+    torch.cuda.empty_cache()
+    return rec
 
 
 def run_small_graph(a, shape, dev, peak):
@@ -991,6 +1048,7 @@ def main():
     ap.add_argument("--no-clustered", action="store_true", help="skip the clustered-graph sub-record (N = 1)")
     ap.add_argument("--no-products", action="store_true", help="skip the products-shape sub-record")
     ap.add_argument("--no-arxiv", action="store_true", help="skip the arxiv-shape sub-record (N = 1)")
+    ap.add_argument("--no-column-sharded", action="store_true", help="skip the column-sharded sub-record (N > 1)")
     ap.add_argument("--workload", default="spmm", choices=["spmm", "inference"],
                     help="spmm = the headline hidden sweep; inference = 2-layer GCN/GIN/SAGE end to end (configs[3])")
     a = ap.parse_args()
