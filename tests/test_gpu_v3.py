@@ -390,6 +390,9 @@ def test_tiny_row_launch_on_a_citation_shaped_graph(gpu_backend, oracle, fmt):
                 got = A.mul(x.cuda())
                 torch.cuda.synchronize()
                 assert torch.equal(got.cpu(), want), (dtype, hidden, fmt, value is not None, sp)
+                if hidden >= 128:      # host operands: column tiles + row-chunk plans of the two-launch family
+                    gpu_backend.plan_set_option(A.sp_info_ptr, "host_chunks", 3)
+                    assert torch.equal(A.mul(x.pin_memory()), want), (dtype, hidden, fmt, value is not None, sp, "host")
                 A.free()
 
 
