@@ -1152,7 +1152,7 @@ PYGIM_API int pygim_wait_flags(const int32_t *flags, int n, int32_t epoch, void 
 // finished rows of tile t-1 download on `sout` while tile t computes on `st`.  Nothing is awaited: the caller joins
 // `sout` into `st` and synchronises - once per call (pygim_spmm_run_group_host) or once per batch of calls
 // (pygim_spmm_run_many_host, where the uploads of call k+1 overlap the kernels of call k as well).
-// `chunk_last`: cut the LAST tile's launch into nnz-balanced row chunks whose downloads follow chunk by chunk, so
+// `chunk_last`: cut the launches of the LAST TWO tiles into row chunks whose downloads follow chunk by chunk, so
 // only a fraction of one tile's download is exposed at the end (in a batch: the last call only - every other
 // download already overlaps the kernels that follow it, and a chunked tile costs three extra launches).
 static int host_enqueue(Group *g, int n_ds, const void *const *B_parts, const int64_t *ldb, void *C, int64_t ldc,
@@ -1225,7 +1225,24 @@ static int host_enqueue(Group *g, int n_ds, const void *const *B_parts, const in
         n_chunks = g->opt_host_chunks > 0 ? (int)g->opt_host_chunks : 4;
         if (g->parts[0].chunks.size() != (size_t)n_chunks) {
             std::vector<int64_t> split((size_t)n_chunks + 1);
-            int rc = pygim_partition_rows_by_nnz(g->parts[0].h_rowptr.data(), g->parts[0].nrows, n_chunks, split.data());
+            int rc = PYGIM_OK;
+            if (g->opt_host_chunks > 0) {
+                rc = pygim_partition_rows_by_nnz(g->parts[0].h_rowptr.data(), g->parts[0].nrows, n_chunks, split.data());
+            } else {
+                // automatic: shrinking chunks (40 / 30 / 20 / 10 % of the nonzeros) - only the LAST chunk's download is
+                // exposed, so it should be the smallest, while four equal launches' worth of kernel efficiency is kept
+                const std::vector<int> &rp = g->parts[0].h_rowptr;
+                const long long rows = g->parts[0].nrows, total = (long long)(unsigned)rp[(size_t)rows];
+                const double cum[5] = {0.0, 0.4, 0.7, 0.9, 1.0};
+                split[0] = 0;
+                for (int k = 1; k < 4; ++k) {
+                    const long long target = (long long)(cum[k] * (double)total);
+                    const long long r = std::lower_bound(rp.begin(), rp.begin() + rows + 1, target,
+                                                         [](int v, long long t) { return (long long)(unsigned)v < t; }) - rp.begin();
+                    split[(size_t)k] = std::min<long long>(rows, std::max<long long>(r, split[(size_t)k - 1]));
+                }
+                split[4] = rows;
+            }
             if (rc) return rc;
             for (auto &p : g->parts) {
                 for (auto &c : p.chunks) free_plan(c);
@@ -1271,7 +1288,9 @@ static int host_enqueue(Group *g, int n_ds, const void *const *B_parts, const in
         CUDA_TRY(cudaStreamWaitEvent(st, uploaded[t], 0));
         if (t == 0) CUDA_TRY(cudaEventRecord(g->ev[1], st));          // first tile on the device: kernels start
         const bool last = t + 1 == tiles.size();
-        const int chunks_here = (last && chunk_last) ? n_chunks : 1;
+        // the last TWO tiles are cut into row chunks: the download stream must be idle when the last tile's chunks
+        // arrive, so the tile before it has to start downloading while it still computes
+        const int chunks_here = (chunk_last && t + 2 >= tiles.size()) ? n_chunks : 1;
         for (int k = 0; k < chunks_here; ++k) {
             long long brow = 0;
             for (size_t i = 0; i < g->parts.size(); ++i) {            // sparse part 0 overwrites, parts >= 1 add
