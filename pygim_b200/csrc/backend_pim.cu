@@ -315,7 +315,9 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
     // were reordered for locality) or an explicit super_nnz: ~8 per SM, at least 2048 nonzeros, at most 256 K.
     long long super = g.opt_super_nnz;
     if (super <= 0) {
-        if (g.d_row_map != nullptr || !p.hot_super_rows.empty())
+        // (measured on the clustered Reddit-shape graph: the SM-affine schedule wins 2-4 % with dense rows of 256 bytes
+        // and more and loses 12-24 % below - 64 / 128-byte rows are bound by L1 tag lookups, not by the crossbar)
+        if ((g.d_row_map != nullptr && widest_tile_bytes(g) >= 256) || !p.hot_super_rows.empty())
             super = std::min<long long>(262144, std::max<long long>(2048, (short_nnz + seg_nnz) / std::max(1, g_ctx.sm_count * 8)));
         else
             super = (1LL << 60);
