@@ -209,7 +209,8 @@ def kernel_options(stats: GraphStats, hidden: int, elem_size: int, reordered: bo
     short = stats.mean_degree < 96
     # kernel family: deep (128 registers, 16 gathers in flight) for long rows, light (64 registers, twice the warps)
     # for short rows; measured: Reddit-shape 9290 vs 8500 GFLOP/s, products-shape 2314 vs 2656
-    # very short rows (citation graphs, mean degree < 12): one lane group per row (arxiv-shape 0.115 vs 0.146 ms)
+    # very short rows (citation graphs, mean degree < 12): the two-launch family - tiny rows by lane groups, the rest as
+    # pieces (arxiv-shape H = 32: 36 vs 70 us)
     opts["short_rows"] = (4 if stats.mean_degree < 12 else 3) if short else 0
     # work items: ~256 nonzeros, fewer on small graphs so that every resident warp still gets about four items
     # (the library's own default, csrc/backend_pim.cu::build_plan_range)
@@ -217,11 +218,9 @@ def kernel_options(stats: GraphStats, hidden: int, elem_size: int, reordered: bo
     while item * 2 <= want and item < 256:
         item *= 2
     opts["item_nnz"] = item
-    if reordered:
-        # rows that share neighbours are adjacent: let an SM's warps share one superticket's working set, and keep
-        # a gathered chunk to one 128-byte L1 line per dense row so the community's rows fit the L1
-        if hidden * elem_size > 128 and not short:
-            opts["max_g"] = 8
+    # (reordered plans: the library itself schedules SM-affine supertickets when the dense rows are >= 256 bytes.
+    # Capping the lanes per row at 8 - one 128-byte L1 line per gathered row, so a community's rows fit the L1 -
+    # was measured on the clustered Reddit-shape graph and LOSES: 1.79 vs 1.47 ms at H = 64.)
     return opts
 
 
