@@ -130,7 +130,10 @@ PYGIM_API int pygim_spmm_free_group(pygim_handle_t handle);
  *                    (multiple of 128; default 256: narrower 2-D PCIe copies lose a third of the rate when both
  *                    directions are busy)
  *   l2_persist       1/0 forces / forbids the access-policy window (persisting L2 lines) over the dense tile of a
- *                    launch; automatic = on when the tile fits the carve-out */
+ *                    launch; automatic = on when the tile fits the carve-out and every feature row is gathered >= 200
+ *                    times per launch (it halves a long launch's DRAM traffic at equal time, but the pinned lines
+ *                    slow down short launches that alternate between operands: 1/8 Reddit-shape shard sweep 1166 vs
+ *                    913 us) */
 PYGIM_API int pygim_plan_set_option(pygim_handle_t handle, const char *key, int64_t value);
 
 /* Graph statistics the retargeted autotuner consumes (the role of pim_ops.prepare_tune_csr,

@@ -563,12 +563,17 @@ static int run_tile(Group *g, SparsePart &p, const char *B, long long ldb, char 
     const size_t s = dtype_size(g->dtype);
     if (ldb < 0 || (unsigned long long)ldb * s >= (1ull << 32))
         return fail(PYGIM_ERR_INVALID, "row stride of the dense operand must be below 4 GiB");
-    // default: on when the tile the launch gathers from fits the persisting carve-out (Reddit-shape: DRAM traffic
-    // of a 64-column launch 0.97 -> 0.61 GB, of the two H = 128 tiles 3.65 -> 1.64 GB; B >> L2 gains nothing)
+    // Access-policy window (persisting L2 lines) over the tile the launch gathers from.  It halves the DRAM traffic of
+    // a long launch (Reddit-shape, 64-column tile of H = 128: 1.91 -> 0.88 GB) without changing its time (sweep 9407 vs
+    // 9404 GFLOP/s), but the lines it pins outlive the launch: when the next launch gathers from ANOTHER operand -
+    // every sweep, every layer - they crowd the carve-out, and a short launch cannot amortise that.  Measured on a
+    // 1/8 Reddit-shape row shard (what each GPU runs at N = 8), hidden sweep as one CUDA graph: 1166 us with the
+    // window, 913 us without.  So: automatic = on only when the tile fits the carve-out AND every feature row is
+    // gathered at least 200 times by the launch (whole Reddit-shape: 492; a 1/4 shard: 123); "l2_persist" forces it.
     const size_t touched = (size_t)p.ncols * (size_t)width * s;
     const bool persist = g->opt_l2_persist > 0 ||
                          (g->opt_l2_persist < 0 && touched >= (size_t)(4u << 20) &&
-                          (double)touched <= 0.9 * (double)g_ctx.persisting_set);
+                          (double)touched <= 0.9 * (double)g_ctx.persisting_set && p.nnz >= 200 * std::max<long long>(p.ncols, 1));
     if (persist) set_l2_window(stream, B, (size_t)p.ncols * (size_t)ldb * s, touched);
     struct WindowGuard {      // the stream belongs to the caller: never leave our policy window behind
         cudaStream_t st; bool on;
