@@ -8,14 +8,23 @@ value-less adjacency => ones, features = randint(-8, 4) as spmm_test.py:70), FLT
 sweep 16/32/64/128.  One STEP = one pass of the hot path over the sweep (four SpMMs).
 
 metric  : SpMM GFLOP/s = sum_H 2*nnz*H / time (whole job, all GPUs), inputs resident in HBM.
-e2e     : the same step through the public API `prepare_pim_spmm(...).mul(x)` with HOST (pinned) operands:
-          H2D of B and D2H of C inside the timed region.
-roofline: HBM bound for the dominant kernel (the H=128 launch): algorithmic bytes
-          4(N+1) + 4 nnz + s nnz + s N H + s N H / its CUDA-event duration, against
-          MEASURED_PEAKS.json's hbm_gbs.
-N > 1   : the adjacency is row-sharded by nnz across ranks (one process per GPU), B replicated, every
-          rank computes its C row block and the blocks are all-gathered over NCCL; the collective is inside
-          the timed region ("scaling": "strong").
+e2e     : the same step through the plugin with HOST (pinned) operands, H2D of B and D2H of C inside the timed
+          region: at N = 1 the sweep is one call of the batch host entry point (pygim_spmm_run_many_host: one
+          upload / compute / download pipeline), at N > 1 every rank uploads its row block of B, the blocks are
+          all-gathered over NVLink and the rank's rows of C go back.
+roofline: HBM bound for the dominant kernel instantiation (the 64-column-tile kernel: the H = 64 launch and the
+          two H = 128 tile launches): algorithmic bytes 4(N+1) + 4 nnz + s nnz + s N H + s N H / its
+          CUDA-event duration, against MEASURED_PEAKS.json's hbm_gbs; `gather` = the L2 -> SM rate against the
+          measured ceiling of random row gathers.
+N > 1   : the adjacency is row-sharded by nnz across ranks (one process per GPU), B replicated, every rank
+          computes its C row block and stores every finished row into every GPU's copy of C from the kernel's
+          epilogue (NVLink multimem / peer stores, in-kernel arrival flags; `--gather nccl` = one NCCL all-gather
+          instead); the exchange is inside the timed region ("scaling": "strong"), `no_exchange` reports the
+          step without it.
+sub-records of the same line: `clustered` (block-model graph: natural / reordered / hot-cold tiles), `products`
+          (configs[4], with the speed-up against one GPU of the same box at N > 1), `arxiv` (configs[0], CUDA-graph
+          replay, whole-matrix parity; N = 1), `column_sharded` (N > 1), `selftest_multi` (N > 1), and
+          `parity_all_ranks`: every rank checks sampled rows of EVERY rank's block against the oracle.
 --impl reference : the reference's CPU path (`--version=cpu`: row-parallel CSR SpMM on the host cores,
           restated in oracle/spmm_oracle.c because torch_sparse is not installable) on a bounded sample.
 """
