@@ -276,9 +276,9 @@ static int build_plan_range(const Group &g, const SparsePart &p, int seg_len, lo
     for (long long r = r0; r < r1; ++r) {
         const long long s = (unsigned)rp[r], e = (unsigned)rp[r + 1];
         const long long n = e - s;
-        if (tiny_split && n <= seg_len) {
-            // rows of at most kTinyRow nonzeros belong to csr_tiny_rows_kernel; every other uncut row is ONE piece
-            // that stores its row directly (long_idx = ~row: no partial sum, no merge)
+        if (tiny_split && (n <= seg_len || n <= (long long)pygim::kTinyRow)) {
+            // rows of at most kTinyRow nonzeros belong to csr_tiny_rows_kernel (whatever seg_len says); every other
+            // uncut row is ONE piece that stores its row directly (long_idx = ~row: no partial sum, no merge)
             if (n > (long long)pygim::kTinyRow) {
                 Seg sg;
                 sg.long_idx = ~(int)(r - r0);

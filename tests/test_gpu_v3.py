@@ -413,7 +413,7 @@ def test_tiny_row_family_with_a_row_map_and_options(gpu_backend, oracle):
                 if reorder:
                     args.reorder = reorder
                 A = prepare_pim_spmm(adj.to("cuda"), args)
-                for opts in (dict(short_rows=4), dict(short_rows=4, seg_len=32, super_nnz=4096), dict(short_rows=4, cta_threads=512),
+                for opts in (dict(short_rows=4), dict(short_rows=4, seg_len=32, super_nnz=4096), dict(short_rows=4, seg_len=4), dict(short_rows=4, cta_threads=512),
                              dict(short_rows=3), dict(short_rows=4)):
                     for k, v in opts.items():
                         gpu_backend.plan_set_option(A.sp_info_ptr, k, v)
