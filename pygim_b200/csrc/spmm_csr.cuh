@@ -9,12 +9,16 @@
 //    row (the reference's second-level balancing, partition_tsklt_by_nnz_csr,
 //    support/partition.c:186-229).  Consecutive items are bundled into SUPERTICKETS of near-equal
 //    nnz;
-//  * the grid is PERSISTENT and SM-AFFINE: SM s owns supertickets s, s + #SMs, s + 2 #SMs ... and
-//    every warp resident on it drains the same superticket (one atomic per item on the
-//    superticket's own counter), so the warps that share an SM's L1 work on neighbouring rows - with a locality
-//    preserving row order (prepare-time clustering, see pygim_b200/reorder.py) the dense rows they
-//    gather are L1 hits instead of L2 -> SM traffic.  Warps that run out of home work STEAL items
-//    from any unfinished superticket, so no warp idles while another still owns a long row;
+//  * the grid is PERSISTENT.  Default plans are ONE queue of items (exactly balanced; the first round is dealt
+//    statically, warp w takes item w).  Plans whose rows were reordered for locality (pygim_b200/reorder.py) and
+//    whose dense rows are >= 256 bytes are SM-AFFINE: SM s owns supertickets s, s + #SMs, s + 2 #SMs ... and every
+//    warp resident on it drains the same superticket (one atomic per item on the superticket's own counter), so
+//    the warps that share an SM's L1 work on neighbouring rows and the dense rows they gather are L1 hits instead
+//    of L2 -> SM traffic.  Warps that run out of home work STEAL items from any unfinished superticket, so no
+//    warp idles while another still owns a long row;
+//  * citation-shaped graphs (mean degree < 12) are split at plan time: rows of <= 8 nonzeros go to
+//    csr_tiny_rows_kernel (one lane group per row, a grid as wide as the matrix), every other row is a list of
+//    <= seg_len pieces drawn longest first by this kernel (STREAM == 2);
 //  * a dense row of H elements is covered by G lanes, each moving one 16-byte word (float4,
 //    16 x int8, ...), so P = 32/G nonzeros are gathered by every load instruction.  Every lane
 //    group reads the column indices (and values) of ITS OWN four consecutive nonzeros as one
