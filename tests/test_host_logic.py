@@ -115,6 +115,11 @@ def test_choose_ds_parts():
     assert autotuner.choose_ds_parts(232_965, 128, 4, l2) == 2       # 119 MB does not: two 64-column tiles
     assert autotuner.choose_ds_parts(2_449_029, 128, 4, l2) == 1     # products-shape: B >> L2, tiling cannot help
     assert autotuner.choose_ds_parts(1000, 32, 4, l2) == 1
+    # a feature row gathered fewer than 32 times per launch has nothing to keep resident: no tiling (arxiv-shape
+    # H = 128 is 86 MB, above the budget, but runs as one tile); with enough reuse the size rule decides
+    assert autotuner.choose_ds_parts(169_343, 128, 4, l2) == 2
+    assert autotuner.choose_ds_parts(169_343, 128, 4, l2, nnz=1_166_243) == 1
+    assert autotuner.choose_ds_parts(232_965, 128, 4, l2, nnz=114_615_892) == 2
 
 
 def test_space_algebra():
